@@ -1,0 +1,849 @@
+// pgcn_b200.cu — C-ABI implementation (see include/pgcn_b200.h for the contract and the
+// reference file:line each entry point replaces).
+//
+// Host side of the hot path: plan construction (device CSR copies, row-block schedule, boundary
+// CSR for the gradient scatter-add), kernel dispatch, and the two transports of the halo
+// exchange (NCCL grouped send/recv resolved at run time from the process's libnccl, and the
+// peer-memory path that stores rows directly into the neighbour GPU's slab over NVLink).
+#include "../../include/pgcn_b200.h"
+#include "spmm_kernels.cuh"
+
+#include <dlfcn.h>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pgcn;
+
+// ------------------------------------------------------------------------------------------
+// NCCL, resolved lazily from whatever libnccl the process already has (torch's bundled copy),
+// so this library has no link-time NCCL dependency and loads on a box without it.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess_ = 0, ncclFloat_ = 7 };
+
+struct NcclApi {
+    bool tried = false, ok = false;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+bool load_nccl()
+{
+    if (g_nccl.tried) return g_nccl.ok;
+    g_nccl.tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);  // torch's copy, if loaded
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return false;
+#define PGCN_SYM(field, name)                                              \
+    *(void**)(&g_nccl.field) = dlsym(h, name);                             \
+    if (!g_nccl.field) return false;
+    PGCN_SYM(GetUniqueId, "ncclGetUniqueId")
+    PGCN_SYM(CommInitRank, "ncclCommInitRank")
+    PGCN_SYM(CommDestroy, "ncclCommDestroy")
+    PGCN_SYM(Send, "ncclSend")
+    PGCN_SYM(Recv, "ncclRecv")
+    PGCN_SYM(GroupStart, "ncclGroupStart")
+    PGCN_SYM(GroupEnd, "ncclGroupEnd")
+    PGCN_SYM(GetErrorString, "ncclGetErrorString")
+#undef PGCN_SYM
+    g_nccl.ok = true;
+    return true;
+}
+
+std::string g_lib_error = "";
+
+constexpr int kMaxPeers = 16;
+
+struct DevCsr {
+    int nrows = 0;
+    int64_t nnz = 0;
+    std::vector<int> h_rowptr;      // kept for (re)building schedules
+    int* d_rowptr = nullptr;
+    int* d_colidx = nullptr;
+    float* d_vals = nullptr;
+    // schedule
+    int4* d_blocks = nullptr;
+    int nblocks = 0;
+    int4* d_long = nullptr;
+    int nlong = 0;
+    int nslots = 0;
+    float* d_partial = nullptr;
+    int64_t sched_epb = -1, sched_long = -1;
+};
+
+struct P2PBlob {                     // what pgcn_p2p_export writes (PGCN_P2P_HANDLE_BYTES)
+    cudaIpcMemHandle_t ipc;          // 64 bytes
+    int64_t arena_bytes;
+    int64_t off_flags, off_fwd[2], off_bwd[2];
+    int32_t k, rank, f_max, pad;
+    int64_t send_off[kMaxPeers + 1];
+    int64_t recv_off[kMaxPeers + 1];
+};
+static_assert(sizeof(P2PBlob) <= PGCN_P2P_HANDLE_BYTES, "blob too large");
+
+}  // namespace
+
+struct pgcn_plan {
+    int device = 0;
+    int m = 0, h = 0, k = 1, rank = 0, f_max = 0;
+    int64_t S = 0;
+    DevCsr fwd, tr, own, halo;       // halo: compact rows, see halo_rowmap
+    int* d_halo_rowmap = nullptr;    // rows of `halo` -> local row ids
+    bool have_split = false;
+    int64_t cols_ref = 0, rows_ref_t = 0;
+
+    std::vector<int64_t> send_off, recv_off;
+    int* d_send_idx = nullptr;
+    // boundary CSR for unpack_add
+    int* d_brow = nullptr; int* d_bptr = nullptr; int* d_bpos = nullptr; int nb = 0;
+
+    // slabs (local transport)
+    float* d_send_slab = nullptr;    // S x f_max
+    float* d_halo_slab = nullptr;    // h x f_max   (forward receive)
+    float* d_rrecv_slab = nullptr;   // S x f_max   (reverse receive)
+    float* d_hsend_slab = nullptr;   // h x f_max   (reverse send: halo partials of A^T g)
+
+    // options
+    int64_t opt_epb = 256, opt_long = 0, opt_tile = 0, opt_unroll = 0, opt_overlap = 1;
+
+    // NCCL
+    ncclComm_t comm = nullptr;
+    cudaStream_t comm_stream = nullptr;
+    cudaStream_t host_stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+
+    // peer-memory transport
+    bool p2p = false;
+    void* arena = nullptr; int64_t arena_bytes = 0;
+    int64_t off_flags = 0, off_fwd[2] = {0, 0}, off_bwd[2] = {0, 0};
+    void* peer_arena[kMaxPeers] = {nullptr};
+    P2PBlob peer_blob[kMaxPeers];
+    unsigned long long epoch = 0;
+
+    // host-buffer variant
+    float* d_hostH = nullptr; float* d_hostZ = nullptr; int64_t host_cap = 0;
+
+    int64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(pgcn_plan* p, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (p) p->err = buf; else g_lib_error = buf;
+    return code;
+}
+
+#define CU(p, expr)                                                                         \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            return fail(p, PGCN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                   \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                       \
+    } while (0)
+
+#define NC(p, expr)                                                                         \
+    do {                                                                                    \
+        int e__ = (expr);                                                                   \
+        if (e__ != ncclSuccess_)                                                            \
+            return fail(p, PGCN_ERR_NCCL, "%s failed: %s", #expr, g_nccl.GetErrorString(e__)); \
+    } while (0)
+
+template <class T>
+int upload(pgcn_plan* p, T** dst, const T* src, size_t n)
+{
+    *dst = nullptr;
+    CU(p, cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) CU(p, cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int csr_upload(pgcn_plan* p, DevCsr& c, int nrows, const int* rowptr, const int* colidx, const float* vals)
+{
+    c.nrows = nrows;
+    c.h_rowptr.assign(rowptr, rowptr + nrows + 1);
+    c.nnz = rowptr[nrows];
+    int rc;
+    if ((rc = upload(p, &c.d_rowptr, rowptr, (size_t)nrows + 1))) return rc;
+    if ((rc = upload(p, &c.d_colidx, colidx, (size_t)c.nnz))) return rc;
+    if ((rc = upload(p, &c.d_vals, vals, (size_t)c.nnz))) return rc;
+    return 0;
+}
+
+void csr_free(DevCsr& c)
+{
+    cudaFree(c.d_rowptr); cudaFree(c.d_colidx); cudaFree(c.d_vals);
+    cudaFree(c.d_blocks); cudaFree(c.d_long); cudaFree(c.d_partial);
+    c = DevCsr();
+}
+
+// Cut [0, nrows) into row blocks of about `epb` nnz (at most kMaxRowsPerBlock rows); rows longer
+// than `long_row` become ceil(deg/epb) single-row segments with a slot each in the side buffer.
+constexpr int kMaxRowsPerBlock = 128;
+
+int build_schedule(pgcn_plan* p, DevCsr& c)
+{
+    const int64_t epb = std::max<int64_t>(p->opt_epb, 8);
+    const int64_t long_row = p->opt_long > 0 ? p->opt_long : 4 * epb;
+    if (c.sched_epb == epb && c.sched_long == long_row) return 0;
+
+    std::vector<int4> blocks, longs;
+    blocks.reserve((size_t)(c.nnz / epb + c.nrows / kMaxRowsPerBlock + 16));
+    int nslots = 0;
+    const int* rp = c.h_rowptr.data();
+    int cur_begin = 0;         // first row of the open block
+    int64_t cur_edges = 0;
+    auto close = [&](int row_end) {
+        if (row_end > cur_begin)
+            blocks.push_back(make_int4(cur_begin, row_end - cur_begin, rp[cur_begin], rp[row_end]));
+        cur_begin = row_end;
+        cur_edges = 0;
+    };
+    for (int r = 0; r < c.nrows; ++r) {
+        const int64_t d = (int64_t)rp[r + 1] - rp[r];
+        if (d > long_row) {
+            close(r);
+            const int nseg = (int)((d + epb - 1) / epb);
+            longs.push_back(make_int4(r, nslots, nseg, 0));
+            for (int s = 0; s < nseg; ++s) {
+                const int e0 = rp[r] + (int)(s * epb);
+                const int e1 = (int)std::min<int64_t>((int64_t)rp[r + 1], (int64_t)e0 + epb);
+                blocks.push_back(make_int4(r, -(nslots + 1), e0, e1));
+                ++nslots;
+            }
+            cur_begin = r + 1;
+            continue;
+        }
+        if (cur_edges > 0 && cur_edges + d > epb) close(r);
+        cur_edges += d;
+        if (r + 1 - cur_begin >= kMaxRowsPerBlock) close(r + 1);
+    }
+    close(c.nrows);
+
+    cudaFree(c.d_blocks); cudaFree(c.d_long); cudaFree(c.d_partial);
+    c.d_blocks = nullptr; c.d_long = nullptr; c.d_partial = nullptr;
+    int rc;
+    if ((rc = upload(p, &c.d_blocks, blocks.data(), blocks.size()))) return rc;
+    if ((rc = upload(p, &c.d_long, longs.data(), longs.size()))) return rc;
+    CU(p, cudaMalloc((void**)&c.d_partial, std::max<size_t>((size_t)nslots * p->f_max, 1) * sizeof(float)));
+    c.nblocks = (int)blocks.size();
+    c.nlong = (int)longs.size();
+    c.nslots = nslots;
+    c.sched_epb = epb;
+    c.sched_long = long_row;
+    return 0;
+}
+
+// ---- kernel dispatch ---------------------------------------------------------------------
+
+struct TileCfg { int lpe, vpl, vw, u, tiles; };
+
+int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+TileCfg choose_tile(const pgcn_plan* p, int f)
+{
+    TileCfg t;
+    t.vw = (f % 4 == 0) ? 4 : 1;
+    const int nvec = f / t.vw;
+    int tile_vecs = nvec;
+    if (p->opt_tile > 0) tile_vecs = std::max<int>(1, (int)std::min<int64_t>(nvec, p->opt_tile / t.vw));
+    tile_vecs = std::min(tile_vecs, 128);
+    t.lpe = std::max(4, std::min(32, pow2ceil(tile_vecs)));
+    int vpl = (tile_vecs + t.lpe - 1) / t.lpe;
+    t.vpl = vpl <= 1 ? 1 : (vpl <= 2 ? 2 : 4);
+    t.tiles = (nvec + t.lpe * t.vpl - 1) / (t.lpe * t.vpl);
+    int u = (int)p->opt_unroll;
+    if (u != 2 && u != 4 && u != 8) u = std::max(2, 8 / t.vpl);
+    if (t.vw == 1) u = 4;
+    t.u = std::min(u, t.lpe);
+    return t;
+}
+
+typedef void (*spmm_fn)(const SpmmArgs);
+
+template <int LPE, int VPL, int VW>
+spmm_fn pick_u(int u)
+{
+    if (VW == 1) return spmm_rowblock_kernel<LPE, VPL, VW, 4>;
+    switch (u) {
+        case 2: return spmm_rowblock_kernel<LPE, VPL, VW, 2>;
+        case 8: return spmm_rowblock_kernel<LPE, VPL, VW, (LPE >= 8 ? 8 : 4)>;
+        default: return spmm_rowblock_kernel<LPE, VPL, VW, 4>;
+    }
+}
+
+template <int LPE, int VW>
+spmm_fn pick_vpl(int vpl, int u)
+{
+    switch (vpl) {
+        case 1: return pick_u<LPE, 1, VW>(u);
+        case 2: return pick_u<LPE, 2, VW>(u);
+        default: return pick_u<LPE, 4, VW>(u);
+    }
+}
+
+template <int VW>
+spmm_fn pick_lpe(int lpe, int vpl, int u)
+{
+    switch (lpe) {
+        case 4: return pick_vpl<4, VW>(vpl, u);
+        case 8: return pick_vpl<8, VW>(vpl, u);
+        case 16: return pick_vpl<16, VW>(vpl, u);
+        default: return pick_vpl<32, VW>(vpl, u);
+    }
+}
+
+int launch_spmm(pgcn_plan* p, DevCsr& c, const float* H0, const float* H1, int split,
+                float* Z0, float* Z1, int zsplit, const int* rowmap, int f, int beta, cudaStream_t st)
+{
+    if (c.nrows == 0) return 0;
+    int rc = build_schedule(p, c);
+    if (rc) return rc;
+    const TileCfg t = choose_tile(p, f);
+    SpmmArgs a;
+    a.blocks = c.d_blocks; a.nblocks = c.nblocks; a.nrows = c.nrows;
+    a.rowptr = c.d_rowptr; a.colidx = c.d_colidx; a.vals = c.d_vals;
+    a.H0 = H0; a.H1 = H1; a.split = split;
+    a.Z0 = Z0; a.Z1 = Z1; a.zsplit = zsplit;
+    a.rowmap = rowmap;
+    a.partial = c.d_partial; a.f = f; a.beta = beta;
+    if (c.nblocks > 0) {
+        const int groups_per_cta = kSpmmThreads / t.lpe;
+        dim3 grid((unsigned)((c.nblocks + groups_per_cta - 1) / groups_per_cta), (unsigned)t.tiles);
+        spmm_fn fn = (t.vw == 4) ? pick_lpe<4>(t.lpe, t.vpl, t.u) : pick_lpe<1>(t.lpe, t.vpl, t.u);
+        fn<<<grid, kSpmmThreads, 0, st>>>(a);
+        ++p->launches;
+    }
+    if (c.nlong > 0) {
+        FixupArgs fa;
+        fa.long_rows = c.d_long; fa.nlong = c.nlong; fa.partial = c.d_partial;
+        fa.Z0 = Z0; fa.Z1 = Z1; fa.zsplit = zsplit; fa.rowmap = rowmap; fa.f = f; fa.beta = beta;
+        const long long total = (long long)c.nlong * (f / t.vw);
+        const unsigned grid = (unsigned)((total + 255) / 256);
+        if (t.vw == 4) spmm_fixup_kernel<4><<<grid, 256, 0, st>>>(fa);
+        else spmm_fixup_kernel<1><<<grid, 256, 0, st>>>(fa);
+        ++p->launches;
+    }
+    CU(p, cudaGetLastError());
+    return 0;
+}
+
+int check_f(pgcn_plan* p, int f)
+{
+    if (!p) return fail(nullptr, PGCN_ERR_INVALID, "null plan");
+    if (f <= 0 || f > p->f_max) return fail(p, PGCN_ERR_INVALID, "f=%d outside (0, f_max=%d]", f, p->f_max);
+    return 0;
+}
+
+unsigned grid_for(long long total)
+{
+    long long g = (total + 255) / 256;
+    return (unsigned)std::max<long long>(1, std::min<long long>(g, 148LL * 32));
+}
+
+int launch_pack(pgcn_plan* p, const float* H, float* slab, float* const* peer_dst, int f, cudaStream_t st)
+{
+    if (p->S == 0) return 0;
+    PackArgs a;
+    a.send_idx = p->d_send_idx; a.S = p->S; a.H = H; a.slab = slab; a.k = p->k; a.f = f;
+    a.to_peers = peer_dst != nullptr;
+    for (int i = 0; i <= p->k; ++i) a.send_off[i] = p->send_off[i];
+    for (int i = 0; i < p->k; ++i) a.peer_dst[i] = peer_dst ? peer_dst[i] : nullptr;
+    const int vw = (f % 4 == 0) ? 4 : 1;
+    const unsigned grid = grid_for(p->S * (f / vw));
+    if (vw == 4) pack_rows_kernel<4><<<grid, 256, 0, st>>>(a);
+    else pack_rows_kernel<1><<<grid, 256, 0, st>>>(a);
+    ++p->launches;
+    CU(p, cudaGetLastError());
+    return 0;
+}
+
+int launch_unpack(pgcn_plan* p, const float* recv, float* G, int f, cudaStream_t st)
+{
+    if (p->nb == 0) return 0;
+    UnpackArgs a;
+    a.brow = p->d_brow; a.bptr = p->d_bptr; a.bpos = p->d_bpos; a.nb = p->nb;
+    a.recv = recv; a.G = G; a.f = f;
+    const int vw = (f % 4 == 0) ? 4 : 1;
+    const long long total = (long long)p->nb * (f / vw);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (vw == 4) unpack_add_kernel<4><<<grid, 256, 0, st>>>(a);
+    else unpack_add_kernel<1><<<grid, 256, 0, st>>>(a);
+    ++p->launches;
+    CU(p, cudaGetLastError());
+    return 0;
+}
+
+// ---- transports ----------------------------------------------------------------------------
+
+int nccl_exchange(pgcn_plan* p, const float* send, float* recv, int f, int reverse, cudaStream_t st)
+{
+    if (p->k == 1) return 0;
+    if (!p->comm) return fail(p, PGCN_ERR_STATE, "exchange needs pgcn_comm_init (k=%d)", p->k);
+    const std::vector<int64_t>& so = reverse ? p->recv_off : p->send_off;
+    const std::vector<int64_t>& ro = reverse ? p->send_off : p->recv_off;
+    NC(p, g_nccl.GroupStart());
+    for (int q = 0; q < p->k; ++q) {
+        if (q == p->rank) continue;
+        const int64_t ns = so[q + 1] - so[q], nr = ro[q + 1] - ro[q];
+        if (ns > 0) NC(p, g_nccl.Send(send + (size_t)so[q] * f, (size_t)ns * f, ncclFloat_, q, p->comm, st));
+        if (nr > 0) NC(p, g_nccl.Recv(recv + (size_t)ro[q] * f, (size_t)nr * f, ncclFloat_, q, p->comm, st));
+    }
+    NC(p, g_nccl.GroupEnd());
+    return 0;
+}
+
+float* arena_ptr(void* base, int64_t off) { return reinterpret_cast<float*>(static_cast<char*>(base) + off); }
+
+int p2p_signal_wait(pgcn_plan* p, cudaStream_t st, bool do_signal, bool do_wait)
+{
+    if (do_signal) {
+        FlagPtrs fp;
+        for (int q = 0; q < p->k; ++q)
+            fp.p[q] = reinterpret_cast<unsigned long long*>(static_cast<char*>(p->peer_arena[q]) + p->peer_blob[q].off_flags);
+        p2p_signal_kernel<<<1, 32, 0, st>>>(fp, p->k, p->rank, p->epoch);
+        ++p->launches;
+    }
+    if (do_wait) {
+        const unsigned long long* mine =
+            reinterpret_cast<const unsigned long long*>(static_cast<char*>(p->arena) + p->off_flags);
+        p2p_wait_kernel<<<1, 32, 0, st>>>(mine, p->k, p->rank, p->epoch);
+        ++p->launches;
+    }
+    CU(p, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+const char* pgcn_version(void) { return "pgcn_b200 0.1 (sm_100a, CSR row-block SpMM + halo exchange)"; }
+
+int pgcn_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, PGCN_ERR_NOGPU, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    return n;
+}
+
+const char* pgcn_last_error(const pgcn_plan* plan) { return plan ? plan->err.c_str() : g_lib_error.c_str(); }
+
+int pgcn_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                     int32_t m, int32_t h,
+                     const int32_t* t_rowptr, const int32_t* t_colidx, const float* t_vals,
+                     const int32_t* send_idx, const int64_t* send_off, const int64_t* recv_off,
+                     int32_t k, int32_t rank, int32_t f_max, pgcn_plan** out)
+{
+    if (!out) return fail(nullptr, PGCN_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!rowptr || !t_rowptr || !send_off || !recv_off) return fail(nullptr, PGCN_ERR_INVALID, "null index array");
+    if (m < 0 || h < 0 || k < 1 || rank < 0 || rank >= k || f_max < 1)
+        return fail(nullptr, PGCN_ERR_INVALID, "bad sizes m=%d h=%d k=%d rank=%d f_max=%d", m, h, k, rank, f_max);
+    if (recv_off[k] != h) return fail(nullptr, PGCN_ERR_INVALID, "recv_off[k]=%lld != h=%d", (long long)recv_off[k], h);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, PGCN_ERR_NOGPU, "no CUDA device: the PGCN B200 path has no CPU fallback");
+    }
+    const int64_t nnz = rowptr[m];
+    if (nnz > 0 && (!colidx || !vals || !t_colidx || !t_vals)) return fail(nullptr, PGCN_ERR_INVALID, "null colidx/vals");
+    if (t_rowptr[m + h] != nnz) return fail(nullptr, PGCN_ERR_INVALID, "transpose nnz mismatch");
+    for (int64_t e = 0; e < nnz; ++e) {
+        if (colidx[e] < 0 || colidx[e] >= m + h) return fail(nullptr, PGCN_ERR_INVALID, "colidx[%lld]=%d out of [0,%d)", (long long)e, colidx[e], m + h);
+        if (t_colidx[e] < 0 || t_colidx[e] >= m) return fail(nullptr, PGCN_ERR_INVALID, "t_colidx[%lld]=%d out of [0,%d)", (long long)e, t_colidx[e], m);
+    }
+    const int64_t S = send_off[k];
+    for (int64_t j = 0; j < S; ++j)
+        if (!send_idx || send_idx[j] < 0 || send_idx[j] >= m) return fail(nullptr, PGCN_ERR_INVALID, "send_idx[%lld] out of range", (long long)j);
+
+    pgcn_plan* p = new pgcn_plan();
+    p->m = m; p->h = h; p->k = k; p->rank = rank; p->f_max = f_max; p->S = S;
+    p->send_off.assign(send_off, send_off + k + 1);
+    p->recv_off.assign(recv_off, recv_off + k + 1);
+    cudaGetDevice(&p->device);
+
+#define TRY(expr) do { int rc__ = (expr); if (rc__) { g_lib_error = p->err; pgcn_plan_destroy(p); return rc__; } } while (0)
+    TRY(csr_upload(p, p->fwd, m, rowptr, colidx, vals));
+    TRY(csr_upload(p, p->tr, m + h, t_rowptr, t_colidx, t_vals));
+
+    // distinct referenced columns / transposed rows (for the roofline's compulsory bytes)
+    for (int r = 0; r < m + h; ++r) if (t_rowptr[r + 1] > t_rowptr[r]) ++p->cols_ref;
+    p->rows_ref_t = 0;
+    for (int r = 0; r < m; ++r) if (rowptr[r + 1] > rowptr[r]) ++p->rows_ref_t;
+
+    // split A_local = [A_own | A_halo] (Parallel-GCN/main.c:271 then :295) for exchange/compute overlap
+    if (h > 0 && k > 1) {
+        std::vector<int> o_rp(m + 1, 0), o_ci; std::vector<float> o_v;
+        std::vector<int> h_rp(1, 0), h_ci, h_map; std::vector<float> h_v;
+        o_ci.reserve(nnz); o_v.reserve(nnz);
+        for (int r = 0; r < m; ++r) {
+            const size_t before = h_ci.size();
+            for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+                if (colidx[e] < m) { o_ci.push_back(colidx[e]); o_v.push_back(vals[e]); }
+                else { h_ci.push_back(colidx[e]); h_v.push_back(vals[e]); }
+            }
+            o_rp[r + 1] = (int)o_ci.size();
+            if (h_ci.size() > before) { h_map.push_back(r); h_rp.push_back((int)h_ci.size()); }
+        }
+        TRY(csr_upload(p, p->own, m, o_rp.data(), o_ci.data(), o_v.data()));
+        TRY(csr_upload(p, p->halo, (int)h_map.size(), h_rp.data(), h_ci.data(), h_v.data()));
+        TRY(upload(p, &p->d_halo_rowmap, h_map.data(), h_map.size()));
+        p->have_split = true;
+    }
+
+    TRY(upload(p, &p->d_send_idx, send_idx, (size_t)S));
+    // boundary CSR: for every owned row that appears in some send list, the slab positions
+    {
+        std::vector<std::pair<int, int>> pr((size_t)S);
+        for (int64_t j = 0; j < S; ++j) pr[j] = std::make_pair(send_idx[j], (int)j);
+        std::stable_sort(pr.begin(), pr.end(), [](const std::pair<int,int>& a, const std::pair<int,int>& b) { return a.first < b.first; });
+        std::vector<int> brow, bptr(1, 0), bpos((size_t)S);
+        for (int64_t j = 0; j < S; ++j) {
+            if (j == 0 || pr[j].first != pr[j - 1].first) { if (j) bptr.push_back((int)j); brow.push_back(pr[j].first); }
+            bpos[j] = pr[j].second;
+        }
+        if (S) bptr.push_back((int)S);
+        p->nb = (int)brow.size();
+        TRY(upload(p, &p->d_brow, brow.data(), brow.size()));
+        TRY(upload(p, &p->d_bptr, bptr.data(), bptr.size()));
+        TRY(upload(p, &p->d_bpos, bpos.data(), bpos.size()));
+    }
+    auto slab = [&](float** d, int64_t rows) -> int {
+        CU(p, cudaMalloc((void**)d, std::max<size_t>((size_t)rows * f_max, 1) * sizeof(float)));
+        return 0;
+    };
+    TRY(slab(&p->d_send_slab, S));
+    TRY(slab(&p->d_halo_slab, h));
+    TRY(slab(&p->d_rrecv_slab, S));
+    TRY(slab(&p->d_hsend_slab, h));
+    {
+        cudaError_t e1 = cudaStreamCreateWithFlags(&p->comm_stream, cudaStreamNonBlocking);
+        if (e1 == cudaSuccess) e1 = cudaStreamCreateWithFlags(&p->host_stream, cudaStreamNonBlocking);
+        cudaError_t e2 = cudaEventCreateWithFlags(&p->ev_a, cudaEventDisableTiming);
+        cudaError_t e3 = cudaEventCreateWithFlags(&p->ev_b, cudaEventDisableTiming);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+            fail(p, PGCN_ERR_CUDA, "stream/event creation failed");
+            g_lib_error = p->err; pgcn_plan_destroy(p); return PGCN_ERR_CUDA;
+        }
+    }
+#undef TRY
+    *out = p;
+    return 0;
+}
+
+int pgcn_plan_destroy(pgcn_plan* p)
+{
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    if (p->comm && g_nccl.ok) g_nccl.CommDestroy(p->comm);
+    for (int q = 0; q < kMaxPeers; ++q)
+        if (p->peer_arena[q] && q != p->rank) cudaIpcCloseMemHandle(p->peer_arena[q]);
+    cudaFree(p->arena);
+    csr_free(p->fwd); csr_free(p->tr); csr_free(p->own); csr_free(p->halo);
+    cudaFree(p->d_halo_rowmap); cudaFree(p->d_send_idx);
+    cudaFree(p->d_brow); cudaFree(p->d_bptr); cudaFree(p->d_bpos);
+    cudaFree(p->d_send_slab); cudaFree(p->d_halo_slab); cudaFree(p->d_rrecv_slab); cudaFree(p->d_hsend_slab);
+    cudaFree(p->d_hostH); cudaFree(p->d_hostZ);
+    if (p->comm_stream) cudaStreamDestroy(p->comm_stream);
+    if (p->host_stream) cudaStreamDestroy(p->host_stream);
+    if (p->ev_a) cudaEventDestroy(p->ev_a);
+    if (p->ev_b) cudaEventDestroy(p->ev_b);
+    cudaGetLastError();
+    delete p;
+    return 0;
+}
+
+int pgcn_plan_set_option(pgcn_plan* p, const char* name, int64_t value)
+{
+    if (!p || !name) return fail(p, PGCN_ERR_INVALID, "null argument");
+    const std::string n(name);
+    if (n == "edges_per_block") p->opt_epb = value;
+    else if (n == "long_row") p->opt_long = value;
+    else if (n == "tile_floats") p->opt_tile = value;
+    else if (n == "unroll") p->opt_unroll = value;
+    else if (n == "overlap") p->opt_overlap = value;
+    else return fail(p, PGCN_ERR_INVALID, "unknown option '%s'", name);
+    return 0;
+}
+
+int64_t pgcn_plan_get_option(const pgcn_plan* p, const char* name)
+{
+    if (!p || !name) return PGCN_ERR_INVALID;
+    const std::string n(name);
+    if (n == "edges_per_block") return p->opt_epb;
+    if (n == "long_row") return p->opt_long;
+    if (n == "tile_floats") return p->opt_tile;
+    if (n == "unroll") return p->opt_unroll;
+    if (n == "overlap") return p->opt_overlap;
+    if (n == "p2p") return p->p2p ? 1 : 0;
+    if (n == "nccl") return p->comm ? 1 : 0;
+    if (n == "blocks_fwd") return p->fwd.nblocks;
+    if (n == "long_rows_fwd") return p->fwd.nlong;
+    return PGCN_ERR_INVALID;
+}
+
+void* pgcn_plan_slab(pgcn_plan* p, int which)
+{
+    if (!p) return nullptr;
+    switch (which) {
+        case 0: return p->d_send_slab;
+        case 1: return p->d_halo_slab;
+        case 2: return p->d_rrecv_slab;
+        case 3: return p->d_hsend_slab;
+        default: return nullptr;
+    }
+}
+
+int pgcn_algorithmic_bytes(const pgcn_plan* p, int32_t f, pgcn_bytes* o)
+{
+    if (!p || !o) return PGCN_ERR_INVALID;
+    const int64_t nnz = p->fwd.nnz, m = p->m, h = p->h, S = p->S, F = f;
+    o->nnz = nnz; o->m = m; o->h = h; o->cols_ref = p->cols_ref;
+    o->spmm_fwd = 8 * nnz + 4 * (m + 1) + 4 * F * p->cols_ref + 4 * F * m;
+    o->spmm_bwd = 8 * nnz + 4 * (m + h + 1) + 4 * F * p->rows_ref_t + 4 * F * (m + h);
+    o->gather_fwd = nnz * (8 + 4 * F) + 4 * (m + 1) + 4 * F * m;
+    o->xchg_out = 4 * F * S;
+    o->xchg_in = 4 * F * h;
+    o->pack = 2 * 4 * F * S;
+    return 0;
+}
+
+int64_t pgcn_launch_count(const pgcn_plan* p) { return p ? p->launches : 0; }
+
+// ---- communicator --------------------------------------------------------------------------
+
+int pgcn_comm_unique_id(void* id128)
+{
+    if (!id128) return fail(nullptr, PGCN_ERR_INVALID, "null id buffer");
+    if (!load_nccl()) return fail(nullptr, PGCN_ERR_NCCL, "libnccl.so.2 not found in this process");
+    ncclUniqueId id;
+    NC(nullptr, g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return 0;
+}
+
+int pgcn_comm_init(pgcn_plan* p, const void* id128)
+{
+    if (!p || !id128) return fail(p, PGCN_ERR_INVALID, "null argument");
+    if (!load_nccl()) return fail(p, PGCN_ERR_NCCL, "libnccl.so.2 not found in this process");
+    if (p->comm) return 0;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    CU(p, cudaSetDevice(p->device));
+    NC(p, g_nccl.CommInitRank(&p->comm, p->k, id, p->rank));
+    return 0;
+}
+
+int pgcn_p2p_export(pgcn_plan* p, void* handle_out)
+{
+    if (!p || !handle_out) return fail(p, PGCN_ERR_INVALID, "null argument");
+    if (p->k > kMaxPeers) return fail(p, PGCN_ERR_INVALID, "peer transport supports k <= %d", kMaxPeers);
+    if (!p->arena) {
+        auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
+        int64_t off = 0;
+        p->off_flags = off; off = align(off + (int64_t)kMaxPeers * 8);
+        const int64_t fwd_bytes = align((int64_t)p->h * p->f_max * 4), bwd_bytes = align((int64_t)p->S * p->f_max * 4);
+        for (int i = 0; i < 2; ++i) { p->off_fwd[i] = off; off += std::max<int64_t>(fwd_bytes, 256); }
+        for (int i = 0; i < 2; ++i) { p->off_bwd[i] = off; off += std::max<int64_t>(bwd_bytes, 256); }
+        p->arena_bytes = off;
+        CU(p, cudaMalloc(&p->arena, (size_t)off));
+        CU(p, cudaMemset(p->arena, 0, (size_t)off));
+        CU(p, cudaDeviceSynchronize());
+    }
+    P2PBlob b;
+    memset(&b, 0, sizeof b);
+    CU(p, cudaIpcGetMemHandle(&b.ipc, p->arena));
+    b.arena_bytes = p->arena_bytes; b.off_flags = p->off_flags;
+    for (int i = 0; i < 2; ++i) { b.off_fwd[i] = p->off_fwd[i]; b.off_bwd[i] = p->off_bwd[i]; }
+    b.k = p->k; b.rank = p->rank; b.f_max = p->f_max;
+    for (int i = 0; i <= p->k; ++i) { b.send_off[i] = p->send_off[i]; b.recv_off[i] = p->recv_off[i]; }
+    memset(handle_out, 0, PGCN_P2P_HANDLE_BYTES);
+    memcpy(handle_out, &b, sizeof b);
+    return 0;
+}
+
+int pgcn_p2p_import(pgcn_plan* p, const void* handles_k)
+{
+    if (!p || !handles_k) return fail(p, PGCN_ERR_INVALID, "null argument");
+    if (!p->arena) return fail(p, PGCN_ERR_STATE, "call pgcn_p2p_export first");
+    const char* base = static_cast<const char*>(handles_k);
+    for (int q = 0; q < p->k; ++q) {
+        memcpy(&p->peer_blob[q], base + (size_t)q * PGCN_P2P_HANDLE_BYTES, sizeof(P2PBlob));
+        const P2PBlob& b = p->peer_blob[q];
+        if (b.k != p->k || b.rank != q || b.f_max != p->f_max)
+            return fail(p, PGCN_ERR_INVALID, "peer blob %d inconsistent (k=%d rank=%d f_max=%d)", q, b.k, b.rank, b.f_max);
+        // wire-order invariant: what I send to q is what q expects from me (GPU/PGCN.py:47-48)
+        if (b.recv_off[p->rank + 1] - b.recv_off[p->rank] != p->send_off[q + 1] - p->send_off[q])
+            return fail(p, PGCN_ERR_INVALID, "send/recv count mismatch with peer %d", q);
+        if (q == p->rank) { p->peer_arena[q] = p->arena; continue; }
+        CU(p, cudaIpcOpenMemHandle(&p->peer_arena[q], b.ipc, cudaIpcMemLazyEnablePeerAccess));
+    }
+    p->p2p = true;
+    return 0;
+}
+
+// ---- hot path --------------------------------------------------------------------------------
+
+int pgcn_spmm(pgcn_plan* p, int transpose, const float* H_own, const float* H_halo,
+              float* Z, float* Z_halo, int32_t f, void* stream)
+{
+    int rc = check_f(p, f);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!transpose) {
+        if (p->m > 0 && (!H_own || !Z)) return fail(p, PGCN_ERR_INVALID, "null H_own/Z");
+        if (p->h > 0 && !H_halo) return fail(p, PGCN_ERR_INVALID, "h=%d but H_halo is null", p->h);
+        return launch_spmm(p, p->fwd, H_own, H_halo, p->m, Z, nullptr, p->m, nullptr, f, 0, st);
+    }
+    if (p->m > 0 && (!H_own || !Z)) return fail(p, PGCN_ERR_INVALID, "null gZ/G");
+    if (p->h > 0 && !Z_halo) return fail(p, PGCN_ERR_INVALID, "h=%d but Z_halo is null", p->h);
+    return launch_spmm(p, p->tr, H_own, nullptr, p->m, Z, Z_halo, p->m, nullptr, f, 0, st);
+}
+
+int pgcn_pack(pgcn_plan* p, const float* H, float* send_slab, int32_t f, void* stream)
+{
+    int rc = check_f(p, f);
+    if (rc) return rc;
+    if (p->S > 0 && (!H || !send_slab)) return fail(p, PGCN_ERR_INVALID, "null H/send_slab");
+    return launch_pack(p, H, send_slab, nullptr, f, (cudaStream_t)stream);
+}
+
+int pgcn_exchange(pgcn_plan* p, const float* send_slab, float* recv_slab, int32_t f, int reverse, void* stream)
+{
+    int rc = check_f(p, f);
+    if (rc) return rc;
+    return nccl_exchange(p, send_slab, recv_slab, f, reverse, (cudaStream_t)stream);
+}
+
+int pgcn_unpack_add(pgcn_plan* p, const float* recv_slab, float* G_own, int32_t f, void* stream)
+{
+    int rc = check_f(p, f);
+    if (rc) return rc;
+    if (p->S > 0 && (!recv_slab || !G_own)) return fail(p, PGCN_ERR_INVALID, "null recv_slab/G_own");
+    return launch_unpack(p, recv_slab, G_own, f, (cudaStream_t)stream);
+}
+
+int pgcn_forward(pgcn_plan* p, const float* H_own, float* Z, int32_t f, void* stream)
+{
+    int rc = check_f(p, f);
+    if (rc) return rc;
+    if (p->m > 0 && (!H_own || !Z)) return fail(p, PGCN_ERR_INVALID, "null H_own/Z");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->k == 1)
+        return launch_spmm(p, p->fwd, H_own, p->d_halo_slab, p->m, Z, nullptr, p->m, nullptr, f, 0, st);
+
+    const bool split = p->have_split && p->opt_overlap;
+    if (p->p2p && (f % 4 == 0)) {
+        // peer-memory transport: rows go straight into the neighbours' halo slabs
+        ++p->epoch;
+        const int par = (int)(p->epoch & 1);
+        float* dst[kMaxPeers];
+        for (int q = 0; q < p->k; ++q)
+            dst[q] = arena_ptr(p->peer_arena[q], p->peer_blob[q].off_fwd[par]) + (size_t)p->peer_blob[q].recv_off[p->rank] * f;
+        if ((rc = launch_pack(p, H_own, nullptr, dst, f, st))) return rc;
+        if ((rc = p2p_signal_wait(p, st, true, false))) return rc;
+        float* halo = arena_ptr(p->arena, p->off_fwd[par]);
+        if (split) {
+            if ((rc = launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, nullptr, f, 0, st))) return rc;
+            if ((rc = p2p_signal_wait(p, st, false, true))) return rc;
+            return launch_spmm(p, p->halo, H_own, halo, p->m, Z, nullptr, p->m, p->d_halo_rowmap, f, 1, st);
+        }
+        if ((rc = p2p_signal_wait(p, st, false, true))) return rc;
+        return launch_spmm(p, p->fwd, H_own, halo, p->m, Z, nullptr, p->m, nullptr, f, 0, st);
+    }
+    if (!p->comm) return fail(p, PGCN_ERR_STATE, "k=%d: call pgcn_comm_init or pgcn_p2p_import first", p->k);
+    if (split) {
+        // comm stream: pack -> all-to-all-v ; main stream: own-columns SpMM ; join ; halo-columns SpMM
+        CU(p, cudaEventRecord(p->ev_a, st));
+        CU(p, cudaStreamWaitEvent(p->comm_stream, p->ev_a, 0));
+        if ((rc = launch_pack(p, H_own, p->d_send_slab, nullptr, f, p->comm_stream))) return rc;
+        if ((rc = nccl_exchange(p, p->d_send_slab, p->d_halo_slab, f, 0, p->comm_stream))) return rc;
+        CU(p, cudaEventRecord(p->ev_b, p->comm_stream));
+        if ((rc = launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, nullptr, f, 0, st))) return rc;
+        CU(p, cudaStreamWaitEvent(st, p->ev_b, 0));
+        return launch_spmm(p, p->halo, H_own, p->d_halo_slab, p->m, Z, nullptr, p->m, p->d_halo_rowmap, f, 1, st);
+    }
+    if ((rc = launch_pack(p, H_own, p->d_send_slab, nullptr, f, st))) return rc;
+    if ((rc = nccl_exchange(p, p->d_send_slab, p->d_halo_slab, f, 0, st))) return rc;
+    return launch_spmm(p, p->fwd, H_own, p->d_halo_slab, p->m, Z, nullptr, p->m, nullptr, f, 0, st);
+}
+
+int pgcn_backward(pgcn_plan* p, const float* gZ, float* G_own, int32_t f, void* stream)
+{
+    int rc = check_f(p, f);
+    if (rc) return rc;
+    if (p->m > 0 && (!gZ || !G_own)) return fail(p, PGCN_ERR_INVALID, "null gZ/G_own");
+    cudaStream_t st = (cudaStream_t)stream;
+    // A^T g : rows [0,m) -> G_own, rows [m,m+h) -> halo partials, already in reverse wire order
+    if ((rc = launch_spmm(p, p->tr, gZ, nullptr, p->m, G_own, p->d_hsend_slab, p->m, nullptr, f, 0, st))) return rc;
+    if (p->k == 1) return 0;
+    if (p->p2p && (f % 4 == 0)) {
+        ++p->epoch;
+        const int par = (int)(p->epoch & 1);
+        if (p->h > 0) {
+            PutArgs a;
+            a.src = p->d_hsend_slab; a.k = p->k; a.f = f;
+            for (int q = 0; q <= p->k; ++q) a.off[q] = p->recv_off[q];
+            for (int q = 0; q < p->k; ++q)
+                a.peer_dst[q] = arena_ptr(p->peer_arena[q], p->peer_blob[q].off_bwd[par]) + (size_t)p->peer_blob[q].send_off[p->rank] * f;
+            put_rows_kernel<<<grid_for((long long)p->h * (f / 4)), 256, 0, st>>>(a);
+            ++p->launches;
+            CU(p, cudaGetLastError());
+        }
+        if ((rc = p2p_signal_wait(p, st, true, true))) return rc;
+        return launch_unpack(p, arena_ptr(p->arena, p->off_bwd[par]), G_own, f, st);
+    }
+    if (!p->comm) return fail(p, PGCN_ERR_STATE, "k=%d: call pgcn_comm_init or pgcn_p2p_import first", p->k);
+    if ((rc = nccl_exchange(p, p->d_hsend_slab, p->d_rrecv_slab, f, 1, st))) return rc;
+    return launch_unpack(p, p->d_rrecv_slab, G_own, f, st);
+}
+
+int pgcn_forward_host(pgcn_plan* p, const float* H_host, float* Z_host, int32_t f)
+{
+    int rc = check_f(p, f);
+    if (rc) return rc;
+    if (p->m > 0 && (!H_host || !Z_host)) return fail(p, PGCN_ERR_INVALID, "null host buffer");
+    const int64_t need = (int64_t)p->m * f;
+    if (need > p->host_cap) {
+        cudaFree(p->d_hostH); cudaFree(p->d_hostZ);
+        p->d_hostH = p->d_hostZ = nullptr; p->host_cap = 0;
+        CU(p, cudaMalloc((void**)&p->d_hostH, std::max<size_t>((size_t)need, 1) * 4));
+        CU(p, cudaMalloc((void**)&p->d_hostZ, std::max<size_t>((size_t)need, 1) * 4));
+        p->host_cap = need;
+    }
+    cudaStream_t st = p->host_stream;   // plan-owned non-blocking stream
+    CU(p, cudaMemcpyAsync(p->d_hostH, H_host, (size_t)need * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = pgcn_forward(p, p->d_hostH, p->d_hostZ, f, st))) return rc;
+    CU(p, cudaMemcpyAsync(Z_host, p->d_hostZ, (size_t)need * 4, cudaMemcpyDeviceToHost, st));
+    CU(p, cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

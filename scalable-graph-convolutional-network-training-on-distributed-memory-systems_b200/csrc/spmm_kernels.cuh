@@ -1,0 +1,349 @@
+// spmm_kernels.cuh — sm_100a kernels of the PGCN aggregation path.
+//
+// Replaces, on a B200:
+//   torch.sparse.mm(A, H)        GPU/PGCN.py:127      -> spmm_rowblock_kernel (forward CSR)
+//   torch.sparse.mm(A.t(), g)    GPU/PGCN.py:132      -> spmm_rowblock_kernel (pre-transposed CSR)
+//   H[send_map[p]] per peer      GPU/PGCN.py:104      -> pack_rows_kernel (all peers, one launch)
+//   X[recv_map[p]] = buf         GPU/PGCN.py:115      -> fwd: nothing (SpMM reads the halo slab in place)
+//                                                        bwd: unpack_add_kernel (fixed-order sum)
+//   GrB_mxm PLUS_TIMES_FP32      Parallel-GCN/main.c:271,295
+//
+// The SpMM is an HBM/L2-bound sparse gather-reduce (<= 0.5 flop/byte): no tensor cores.
+// Design:
+//   * the host cuts the row range into "row blocks" of ~equal nnz; one LANE GROUP of LPE lanes
+//     (LPE = 4..32, a sub-warp for narrow feature tiles) walks one block's edge range and keeps
+//     a segmented running sum: the accumulator is flushed each time the edge index crosses a
+//     row boundary, so column indices and values are read fully coalesced (LPE at a time) no
+//     matter how short the rows are;
+//   * each gathered H row segment is read with 16-byte loads by consecutive lanes
+//     (LPE*16 B contiguous = whole 128-B lines for LPE >= 8), U rows in flight per lane group
+//     before the first FMA consumes one (memory-level parallelism);
+//   * rows longer than `long_row` are split into segments that write partial sums to a side
+//     buffer; a second tiny kernel adds the segments in a fixed order (deterministic, no atomics);
+//   * blockIdx.y walks feature tiles, so a wide H can be processed one L2-resident column slice
+//     at a time (tile_floats option) and any f is supported (scalar path when f % 4 != 0).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pgcn {
+
+struct SpmmArgs {
+    const int4* blocks;      // {row_begin, nrows | -(slot+1), e_begin, e_end}
+    int nblocks;
+    int nrows;               // rows of the CSR being multiplied
+    const int* rowptr;       // nrows + 1
+    const int* colidx;
+    const float* vals;
+    const float* H0;         // columns [0, split)
+    const float* H1;         // columns [split, ...)   (halo slab), may be null when unused
+    int split;
+    float* Z0;               // output rows [0, zsplit)
+    float* Z1;               // output rows [zsplit, ...)
+    int zsplit;
+    const int* rowmap;       // optional: output row id = rowmap[row] (compact halo-part CSR)
+    float* partial;          // side buffer for split rows, row stride f
+    int f;                   // feature width == leading dimension of H0/H1/Z0/Z1/partial
+    int beta;                // 0: Z = A*H ; 1: Z += A*H
+};
+
+constexpr int kMaxPeersDev = 16;
+
+template <int VW> struct Vec;
+template <> struct Vec<4> { typedef float4 type; };
+template <> struct Vec<1> { typedef float type; };
+
+__device__ __forceinline__ float4 vzero(float4*) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float vzero(float*) { return 0.f; }
+__device__ __forceinline__ void vfma(float4& a, float w, const float4& r) {
+    a.x = fmaf(w, r.x, a.x); a.y = fmaf(w, r.y, a.y); a.z = fmaf(w, r.z, a.z); a.w = fmaf(w, r.w, a.w);
+}
+__device__ __forceinline__ void vfma(float& a, float w, const float& r) { a = fmaf(w, r, a); }
+__device__ __forceinline__ void vadd(float4& a, const float4& r) { a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w; }
+__device__ __forceinline__ void vadd(float& a, const float& r) { a += r; }
+
+// H rows: read-only path, default L1/L2 allocation (hub rows are re-used).
+__device__ __forceinline__ float4 ld_feat(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_feat(const float* p) { return __ldg(p); }
+// column indices / values: touched once -> streaming, do not displace H rows.
+__device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+// outputs: written once -> streaming stores.
+__device__ __forceinline__ void st_out(float4* p, const float4& v) { __stcs(p, v); }
+__device__ __forceinline__ void st_out(float* p, const float& v) { __stcs(p, v); }
+
+constexpr int kSpmmThreads = 256;
+
+// LPE lanes per edge group, VPL vectors per lane, VW floats per vector, U gathered rows in flight.
+template <int LPE, int VPL, int VW, int U>
+__global__ void __launch_bounds__(kSpmmThreads)
+spmm_rowblock_kernel(const SpmmArgs a)
+{
+    typedef typename Vec<VW>::type vec_t;
+    static_assert(LPE >= U && (LPE % U) == 0, "U must divide LPE");
+    const int lane_w = threadIdx.x & 31;
+    const int gl = threadIdx.x & (LPE - 1);
+    const unsigned gmask = (LPE == 32) ? 0xffffffffu
+                                       : (((1u << (LPE & 31)) - 1u) << (lane_w & ~(LPE - 1)));
+    const int group = (int)((blockIdx.x * (unsigned)kSpmmThreads + threadIdx.x) / LPE);
+    if (group >= a.nblocks) return;           // whole lane groups leave together
+
+    const int4 b = a.blocks[group];
+    const bool seg = b.y < 0;                 // a segment of one split row
+    const int row_stop = seg ? b.x : b.x + b.y;
+    const int e_end = b.w;
+    int e = b.z;
+    int row = b.x;
+
+    // feature tile of this CTA column
+    const int fbase = blockIdx.y * (LPE * VPL * VW);
+    int foff[VPL];
+    bool fok[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        foff[v] = fbase + (v * LPE + gl) * VW;
+        fok[v] = foff[v] < a.f;               // f % VW == 0 is guaranteed by the launcher
+    }
+
+    // row-end lookahead: lane i of the group caches rowptr[rbase + 1 + i]
+    int rbase = row;
+    int rp_cache = 0x7fffffff;
+    int row_end = 0x7fffffff;
+    if (!seg) {
+        const int idx = rbase + 1 + gl;
+        if (idx <= a.nrows) rp_cache = __ldg(a.rowptr + idx);
+        row_end = __shfl_sync(gmask, rp_cache, 0, LPE);
+    }
+
+    vec_t acc[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) acc[v] = vzero((vec_t*)nullptr);
+
+    auto flush_row = [&]() {
+        // write the finished row, clear the accumulator, advance to the next row of the block
+        const int orow = a.rowmap ? __ldg(a.rowmap + row) : row;
+        float* zrow = (orow < a.zsplit) ? a.Z0 + (size_t)orow * a.f
+                                        : a.Z1 + (size_t)(orow - a.zsplit) * a.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (fok[v]) {
+                vec_t* zp = reinterpret_cast<vec_t*>(zrow + foff[v]);
+                if (a.beta) vadd(acc[v], *zp);
+                st_out(zp, acc[v]);
+            }
+            acc[v] = vzero((vec_t*)nullptr);
+        }
+        ++row;
+        int kk = row - rbase;
+        if (kk == LPE) {
+            rbase = row;
+            kk = 0;
+            const int idx = rbase + 1 + gl;
+            rp_cache = (idx <= a.nrows) ? __ldg(a.rowptr + idx) : 0x7fffffff;
+        }
+        row_end = __shfl_sync(gmask, rp_cache, kk, LPE);
+    };
+
+    while (e < e_end) {
+        const int n = min(LPE, e_end - e);
+        int c = 0;
+        float w = 0.f;
+        if (gl < n) {
+            c = ld_stream(a.colidx + e + gl);
+            w = ld_stream(a.vals + e + gl);
+        }
+#pragma unroll
+        for (int j0 = 0; j0 < LPE; j0 += U) {
+            if (j0 >= n) break;               // uniform across the lane group
+            vec_t r[U][VPL];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int cj = __shfl_sync(gmask, c, j0 + u, LPE);
+                if (j0 + u < n) {
+                    const float* hrow = (cj < a.split) ? a.H0 + (size_t)cj * a.f
+                                                       : a.H1 + (size_t)(cj - a.split) * a.f;
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v)
+                        if (fok[v]) r[u][v] = ld_feat(reinterpret_cast<const vec_t*>(hrow + foff[v]));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float wj = __shfl_sync(gmask, w, j0 + u, LPE);
+                if (j0 + u < n) {
+                    const int idx = e + j0 + u;
+                    while (idx >= row_end) flush_row();      // also emits empty rows
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v)
+                        if (fok[v]) vfma(acc[v], wj, r[u][v]);
+                }
+            }
+        }
+        e += n;
+    }
+
+    if (seg) {
+        float* prow = a.partial + (size_t)(-b.y - 1) * a.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (fok[v]) *reinterpret_cast<vec_t*>(prow + foff[v]) = acc[v];
+    } else {
+        while (row < row_stop) flush_row();                   // last row + trailing empty rows
+    }
+}
+
+// Z[row] (+)= sum of the row's segments, in segment order. One thread per (split row, vector).
+struct FixupArgs {
+    const int4* long_rows;   // {row, first_slot, nseg, 0}
+    int nlong;
+    const float* partial;
+    float* Z0; float* Z1; int zsplit;
+    const int* rowmap;
+    int f; int beta;
+};
+
+template <int VW>
+__global__ void __launch_bounds__(256)
+spmm_fixup_kernel(const FixupArgs a)
+{
+    typedef typename Vec<VW>::type vec_t;
+    const int nvec = a.f / VW;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)a.nlong * nvec) return;
+    const int lr = (int)(t / nvec);
+    const int v = (int)(t - (long long)lr * nvec);
+    const int4 d = a.long_rows[lr];
+    const int orow = a.rowmap ? __ldg(a.rowmap + d.x) : d.x;
+    float* zrow = (orow < a.zsplit) ? a.Z0 + (size_t)orow * a.f : a.Z1 + (size_t)(orow - a.zsplit) * a.f;
+    vec_t* zp = reinterpret_cast<vec_t*>(zrow) + v;
+    vec_t s = vzero((vec_t*)nullptr);
+    if (a.beta) s = *zp;
+    for (int i = 0; i < d.z; ++i)
+        vadd(s, reinterpret_cast<const vec_t*>(a.partial + (size_t)(d.y + i) * a.f)[v]);
+    *zp = s;
+}
+
+// send_slab[j, :] = H[send_idx[j], :] ; when `peer_dst` is non-null the row goes straight into the
+// destination rank's halo slab through its NVLink-mapped address (fused pack + transport).
+struct PackArgs {
+    const int* send_idx;       // S
+    long long S;
+    const float* H;
+    float* slab;               // local send slab (used when !to_peers)
+    long long send_off[kMaxPeersDev + 1];
+    float* peer_dst[kMaxPeersDev];   // base of "rows from me" inside peer p's halo slab
+    bool to_peers;
+    int k;
+    int f;
+};
+
+template <int VW>
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const PackArgs a)
+{
+    typedef typename Vec<VW>::type vec_t;
+    const int nvec = a.f / VW;
+    const long long total = a.S * nvec;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long j = t / nvec;
+        const int v = (int)(t - j * nvec);
+        const int src = __ldg(a.send_idx + j);
+        const vec_t val = ld_feat(reinterpret_cast<const vec_t*>(a.H + (size_t)src * a.f) + v);
+        if (!a.to_peers) {
+            reinterpret_cast<vec_t*>(a.slab + (size_t)j * a.f)[v] = val;
+        } else {
+            int p = 0;                                   // k is tiny: linear scan of the offsets
+            while (p + 1 < a.k && j >= a.send_off[p + 1]) ++p;
+            float* base = a.peer_dst[p];
+            reinterpret_cast<vec_t*>(base + (size_t)(j - a.send_off[p]) * a.f)[v] = val;
+        }
+    }
+}
+
+// Plain slab copy into peer memory (reverse direction: the halo partials are already in wire order).
+struct PutArgs {
+    const float* src;            // rows in wire order
+    long long off[kMaxPeersDev + 1];   // row offsets per destination
+    float* peer_dst[kMaxPeersDev];     // destination bases
+    int k; int f;
+};
+
+__global__ void __launch_bounds__(256)
+put_rows_kernel(const PutArgs a)
+{
+    const int nvec = a.f / 4;                              // launcher guarantees f % 4 == 0
+    const long long total = a.off[a.k] * nvec;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long j = t / nvec;
+        const int v = (int)(t - j * nvec);
+        int p = 0;
+        while (p + 1 < a.k && j >= a.off[p + 1]) ++p;
+        const float4 val = __ldcs(reinterpret_cast<const float4*>(a.src + (size_t)j * a.f) + v);
+        reinterpret_cast<float4*>(a.peer_dst[p] + (size_t)(j - a.off[p]) * a.f)[v] = val;
+    }
+}
+
+// Cross-GPU epoch flags for the peer-memory transport.
+// signal: after every store of this stream has been made visible system-wide, write `epoch`
+//         into slot [my_rank] of every peer's flag array.
+// wait  : spin until every peer's slot in MY flag array has reached `epoch`.
+struct FlagPtrs { unsigned long long* p[kMaxPeersDev]; };
+
+__global__ void p2p_signal_kernel(const FlagPtrs peer_flags, int k, int my_rank,
+                                  unsigned long long epoch)
+{
+    __threadfence_system();
+    const int p = threadIdx.x;
+    if (p < k && p != my_rank) {
+        unsigned long long* dst = peer_flags.p[p] + my_rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(epoch) : "memory");
+    }
+}
+
+__global__ void p2p_wait_kernel(const unsigned long long* my_flags, int k, int my_rank,
+                                unsigned long long epoch)
+{
+    const int p = threadIdx.x;
+    if (p < k && p != my_rank) {
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(my_flags + p) : "memory");
+        } while (v < epoch);
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
+// G[brow[i], :] += sum_{q in bpos[bptr[i] .. bptr[i+1])} recv[q, :], in list order.
+struct UnpackArgs {
+    const int* brow;     // nb boundary rows (local ids)
+    const int* bptr;     // nb + 1
+    const int* bpos;     // positions in the recv slab
+    int nb;
+    const float* recv;
+    float* G;
+    int f;
+};
+
+template <int VW>
+__global__ void __launch_bounds__(256)
+unpack_add_kernel(const UnpackArgs a)
+{
+    typedef typename Vec<VW>::type vec_t;
+    const int nvec = a.f / VW;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)a.nb * nvec) return;
+    const int i = (int)(t / nvec);
+    const int v = (int)(t - (long long)i * nvec);
+    const int r = __ldg(a.brow + i);
+    vec_t* gp = reinterpret_cast<vec_t*>(a.G + (size_t)r * a.f) + v;
+    vec_t s = *gp;
+    const int q0 = __ldg(a.bptr + i), q1 = __ldg(a.bptr + i + 1);
+    for (int q = q0; q < q1; ++q)
+        vadd(s, __ldcs(reinterpret_cast<const vec_t*>(a.recv + (size_t)__ldg(a.bpos + q) * a.f) + v));
+    *gp = s;
+}
+
+}  // namespace pgcn
