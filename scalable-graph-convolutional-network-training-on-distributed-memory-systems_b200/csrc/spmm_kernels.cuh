@@ -144,17 +144,26 @@ spmm_rowblock_kernel(const SpmmArgs a)
         row_end = __shfl_sync(gmask, rp_cache, kk, LPE);
     };
 
+    // software pipeline: the (column, value) pair of the NEXT chunk is already in flight while the
+    // current chunk's rows are gathered
+    int c_next = 0;
+    float w_next = 0.f;
+    if (e + gl < e_end) {
+        c_next = ld_stream(a.colidx + e + gl);
+        w_next = ld_stream(a.vals + e + gl);
+    }
     while (e < e_end) {
         const int n = min(LPE, e_end - e);
-        int c = 0;
-        float w = 0.f;
-        if (gl < n) {
-            c = ld_stream(a.colidx + e + gl);
-            w = ld_stream(a.vals + e + gl);
+        const int c = c_next;
+        const float w = w_next;
+        if (e + LPE + gl < e_end) {
+            c_next = ld_stream(a.colidx + e + LPE + gl);
+            w_next = ld_stream(a.vals + e + LPE + gl);
         }
-#pragma unroll
-        for (int j0 = 0; j0 < LPE; j0 += U) {
-            if (j0 >= n) break;               // uniform across the lane group
+        // rolled on purpose: the body (U gathers, U FMAs, U flush sites) stays a few hundred SASS
+        // instructions; fully unrolled it was ~5000 and 1/3 of the issue slots stalled on no_inst
+#pragma unroll 1
+        for (int j0 = 0; j0 < n; j0 += U) {
             vec_t r[U][VPL];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
