@@ -14,7 +14,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libpgcn_b200.so")
+# PGCN_B200_VARIANT=<name> selects lib/libpgcn_b200_<name>.so built with PGCN_B200_DEFS (tuning
+# experiments only, e.g. PGCN_B200_VARIANT=occ0 PGCN_B200_DEFS=-DPGCN_OCC=0); default: no suffix.
+_VARIANT = os.environ.get("PGCN_B200_VARIANT", "")
+LIB = os.path.join(LIBDIR, "libpgcn_b200%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 SOURCES = [os.path.join(CSRC, "pgcn_b200.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, "spmm_kernels.cuh"), os.path.join(ROOT, "include", "pgcn_b200.h")]
 
@@ -48,7 +51,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc not found: cannot build libpgcn_b200.so (no prebuilt library either)")
     os.makedirs(LIBDIR, exist_ok=True)
     tmp = LIB + ".tmp.%d" % os.getpid()
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES + ["-ldl"]
+    defs = os.environ.get("PGCN_B200_DEFS", "").split() if _VARIANT else []
+    cmd = [nvcc] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES + ["-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

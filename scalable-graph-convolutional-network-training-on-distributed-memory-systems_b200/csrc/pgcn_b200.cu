@@ -70,12 +70,15 @@ std::string g_lib_error = "";
 constexpr int kMaxPeers = 16;
 
 struct DevCsr {
-    int nrows = 0;
+    int nrows = 0;                  // rows of the matrix (output rows)
+    int nrows_c = 0;                // non-empty rows = rows the schedule walks
     int64_t nnz = 0;
-    std::vector<int> h_rowptr;      // kept for (re)building schedules
-    int* d_rowptr = nullptr;
-    int* d_colidx = nullptr;
+    std::vector<int> h_rowptr;      // COMPACT row pointers (empty rows squeezed out), for scheduling
+    int* d_colflag = nullptr;       // column | kLastFlag on the last entry of each row
     float* d_vals = nullptr;
+    int* d_rowids = nullptr;        // compact row -> output row, null when the identity
+    int* d_empty = nullptr;         // output rows without entries (zero-filled when beta == 0)
+    int nempty = 0;
     // schedule
     int4* d_blocks = nullptr;
     int nblocks = 0;
@@ -103,7 +106,6 @@ struct pgcn_plan {
     int m = 0, h = 0, k = 1, rank = 0, f_max = 0;
     int64_t S = 0;
     DevCsr fwd, tr, own, halo;       // halo: compact rows, see halo_rowmap
-    int* d_halo_rowmap = nullptr;    // rows of `halo` -> local row ids
     bool have_split = false;
     int64_t cols_ref = 0, rows_ref_t = 0;
 
@@ -179,26 +181,49 @@ int upload(pgcn_plan* p, T** dst, const T* src, size_t n)
     return 0;
 }
 
-int csr_upload(pgcn_plan* p, DevCsr& c, int nrows, const int* rowptr, const int* colidx, const float* vals)
+// Upload one CSR. Rows without entries are squeezed out of the walked row space (their outputs are
+// zero-filled by a separate launch); `ext_rowmap` maps the rows of an already-compact matrix (the
+// halo-column part, which only holds boundary rows) to output rows.
+int csr_upload(pgcn_plan* p, DevCsr& c, int nrows, const int* rowptr, const int* colidx, const float* vals,
+               const std::vector<int>* ext_rowmap = nullptr)
 {
     c.nrows = nrows;
-    c.h_rowptr.assign(rowptr, rowptr + nrows + 1);
     c.nnz = rowptr[nrows];
+    std::vector<int> colflag(colidx, colidx + c.nnz);
+    std::vector<int> rowids, empty;
+    c.h_rowptr.clear();
+    c.h_rowptr.push_back(0);
+    for (int r = 0; r < nrows; ++r) {
+        if (rowptr[r + 1] > rowptr[r]) {
+            colflag[(size_t)rowptr[r + 1] - 1] |= kLastFlag;
+            c.h_rowptr.push_back(rowptr[r + 1]);
+            rowids.push_back(ext_rowmap ? (*ext_rowmap)[r] : r);
+        } else if (!ext_rowmap) {
+            empty.push_back(r);
+        }
+    }
+    c.nrows_c = (int)rowids.size();
+    c.nempty = (int)empty.size();
     int rc;
-    if ((rc = upload(p, &c.d_rowptr, rowptr, (size_t)nrows + 1))) return rc;
-    if ((rc = upload(p, &c.d_colidx, colidx, (size_t)c.nnz))) return rc;
+    if ((rc = upload(p, &c.d_colflag, colflag.data(), (size_t)c.nnz))) return rc;
     if ((rc = upload(p, &c.d_vals, vals, (size_t)c.nnz))) return rc;
+    if (ext_rowmap || c.nempty > 0) {
+        if ((rc = upload(p, &c.d_rowids, rowids.data(), rowids.size()))) return rc;
+    }
+    if (c.nempty > 0) {
+        if ((rc = upload(p, &c.d_empty, empty.data(), empty.size()))) return rc;
+    }
     return 0;
 }
 
 void csr_free(DevCsr& c)
 {
-    cudaFree(c.d_rowptr); cudaFree(c.d_colidx); cudaFree(c.d_vals);
+    cudaFree(c.d_colflag); cudaFree(c.d_vals); cudaFree(c.d_rowids); cudaFree(c.d_empty);
     cudaFree(c.d_blocks); cudaFree(c.d_long); cudaFree(c.d_partial);
     c = DevCsr();
 }
 
-// Cut [0, nrows) into row blocks of about `epb` nnz (at most kMaxRowsPerBlock rows); rows longer
+// Cut the (compact) row range into row blocks of about `epb` nnz (at most kMaxRowsPerBlock rows); rows longer
 // than `long_row` become ceil(deg/epb) single-row segments with a slot each in the side buffer.
 constexpr int kMaxRowsPerBlock = 128;
 
@@ -209,7 +234,7 @@ int build_schedule(pgcn_plan* p, DevCsr& c)
     if (c.sched_epb == epb && c.sched_long == long_row) return 0;
 
     std::vector<int4> blocks, longs;
-    blocks.reserve((size_t)(c.nnz / epb + c.nrows / kMaxRowsPerBlock + 16));
+    blocks.reserve((size_t)(c.nnz / epb + c.nrows_c / kMaxRowsPerBlock + 16));
     int nslots = 0;
     const int* rp = c.h_rowptr.data();
     int cur_begin = 0;         // first row of the open block
@@ -220,7 +245,7 @@ int build_schedule(pgcn_plan* p, DevCsr& c)
         cur_begin = row_end;
         cur_edges = 0;
     };
-    for (int r = 0; r < c.nrows; ++r) {
+    for (int r = 0; r < c.nrows_c; ++r) {
         const int64_t d = (int64_t)rp[r + 1] - rp[r];
         if (d > long_row) {
             close(r);
@@ -239,7 +264,7 @@ int build_schedule(pgcn_plan* p, DevCsr& c)
         cur_edges += d;
         if (r + 1 - cur_begin >= kMaxRowsPerBlock) close(r + 1);
     }
-    close(c.nrows);
+    close(c.nrows_c);
 
     cudaFree(c.d_blocks); cudaFree(c.d_long); cudaFree(c.d_partial);
     c.d_blocks = nullptr; c.d_long = nullptr; c.d_partial = nullptr;
@@ -273,10 +298,11 @@ TileCfg choose_tile(const pgcn_plan* p, int f)
     int vpl = (tile_vecs + t.lpe - 1) / t.lpe;
     t.vpl = vpl <= 1 ? 1 : (vpl <= 2 ? 2 : 4);
     t.tiles = (nvec + t.lpe * t.vpl - 1) / (t.lpe * t.vpl);
-    int u = (int)p->opt_unroll;
-    if (u != 2 && u != 4 && u != 8) u = std::max(2, 8 / t.vpl);
-    if (t.vw == 1) u = 4;
-    t.u = std::min(u, t.lpe);
+    // `unroll` = rows in flight per lane group = 2U (two register buffers of U rows)
+    int u = (int)p->opt_unroll / 2;
+    if (u != 1 && u != 2 && u != 4) u = (t.vpl >= 4) ? 1 : 2;
+    if (t.vw == 1) u = 2;
+    t.u = std::min(u, t.lpe / 2);
     return t;
 }
 
@@ -285,11 +311,11 @@ typedef void (*spmm_fn)(const SpmmArgs);
 template <int LPE, int VPL, int VW>
 spmm_fn pick_u(int u)
 {
-    if (VW == 1) return spmm_rowblock_kernel<LPE, VPL, VW, 4>;
+    if (VW == 1) return spmm_rowblock_kernel<LPE, VPL, VW, 2>;
     switch (u) {
-        case 2: return spmm_rowblock_kernel<LPE, VPL, VW, 2>;
-        case 8: return spmm_rowblock_kernel<LPE, VPL, VW, (LPE >= 8 ? 8 : 4)>;
-        default: return spmm_rowblock_kernel<LPE, VPL, VW, 4>;
+        case 1: return spmm_rowblock_kernel<LPE, VPL, VW, 1>;
+        case 4: return spmm_rowblock_kernel<LPE, VPL, VW, (LPE >= 8 ? 4 : 2)>;
+        default: return spmm_rowblock_kernel<LPE, VPL, VW, 2>;
     }
 }
 
@@ -315,18 +341,27 @@ spmm_fn pick_lpe(int lpe, int vpl, int u)
 }
 
 int launch_spmm(pgcn_plan* p, DevCsr& c, const float* H0, const float* H1, int split,
-                float* Z0, float* Z1, int zsplit, const int* rowmap, int f, int beta, cudaStream_t st)
+                float* Z0, float* Z1, int zsplit, int f, int beta, cudaStream_t st)
 {
     if (c.nrows == 0) return 0;
     int rc = build_schedule(p, c);
     if (rc) return rc;
     const TileCfg t = choose_tile(p, f);
+    if (c.nempty > 0 && !beta) {
+        ZeroArgs za;
+        za.rows = c.d_empty; za.nrows_empty = c.nempty; za.Z0 = Z0; za.Z1 = Z1; za.zsplit = zsplit; za.f = f;
+        const long long total = (long long)c.nempty * (f / t.vw);
+        const unsigned grid = (unsigned)((total + 255) / 256);
+        if (t.vw == 4) zero_rows_kernel<4><<<grid, 256, 0, st>>>(za);
+        else zero_rows_kernel<1><<<grid, 256, 0, st>>>(za);
+        ++p->launches;
+    }
     SpmmArgs a;
-    a.blocks = c.d_blocks; a.nblocks = c.nblocks; a.nrows = c.nrows;
-    a.rowptr = c.d_rowptr; a.colidx = c.d_colidx; a.vals = c.d_vals;
+    a.blocks = c.d_blocks; a.nblocks = c.nblocks;
+    a.colflag = c.d_colflag; a.vals = c.d_vals;
     a.H0 = H0; a.H1 = H1; a.split = split;
     a.Z0 = Z0; a.Z1 = Z1; a.zsplit = zsplit;
-    a.rowmap = rowmap;
+    a.rowids = c.d_rowids;
     a.partial = c.d_partial; a.f = f; a.beta = beta;
     if (c.nblocks > 0) {
         const int groups_per_cta = kSpmmThreads / t.lpe;
@@ -338,7 +373,7 @@ int launch_spmm(pgcn_plan* p, DevCsr& c, const float* H0, const float* H1, int s
     if (c.nlong > 0) {
         FixupArgs fa;
         fa.long_rows = c.d_long; fa.nlong = c.nlong; fa.partial = c.d_partial;
-        fa.Z0 = Z0; fa.Z1 = Z1; fa.zsplit = zsplit; fa.rowmap = rowmap; fa.f = f; fa.beta = beta;
+        fa.Z0 = Z0; fa.Z1 = Z1; fa.zsplit = zsplit; fa.rowids = c.d_rowids; fa.f = f; fa.beta = beta;
         const long long total = (long long)c.nlong * (f / t.vw);
         const unsigned grid = (unsigned)((total + 255) / 256);
         if (t.vw == 4) spmm_fixup_kernel<4><<<grid, 256, 0, st>>>(fa);
@@ -512,8 +547,7 @@ int pgcn_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* 
             if (h_ci.size() > before) { h_map.push_back(r); h_rp.push_back((int)h_ci.size()); }
         }
         TRY(csr_upload(p, p->own, m, o_rp.data(), o_ci.data(), o_v.data()));
-        TRY(csr_upload(p, p->halo, (int)h_map.size(), h_rp.data(), h_ci.data(), h_v.data()));
-        TRY(upload(p, &p->d_halo_rowmap, h_map.data(), h_map.size()));
+        TRY(csr_upload(p, p->halo, (int)h_map.size(), h_rp.data(), h_ci.data(), h_v.data(), &h_map));
         p->have_split = true;
     }
 
@@ -567,7 +601,7 @@ int pgcn_plan_destroy(pgcn_plan* p)
         if (p->peer_arena[q] && q != p->rank) cudaIpcCloseMemHandle(p->peer_arena[q]);
     cudaFree(p->arena);
     csr_free(p->fwd); csr_free(p->tr); csr_free(p->own); csr_free(p->halo);
-    cudaFree(p->d_halo_rowmap); cudaFree(p->d_send_idx);
+    cudaFree(p->d_send_idx);
     cudaFree(p->d_brow); cudaFree(p->d_bptr); cudaFree(p->d_bpos);
     cudaFree(p->d_send_slab); cudaFree(p->d_halo_slab); cudaFree(p->d_rrecv_slab); cudaFree(p->d_hsend_slab);
     cudaFree(p->d_hostH); cudaFree(p->d_hostZ);
@@ -720,11 +754,11 @@ int pgcn_spmm(pgcn_plan* p, int transpose, const float* H_own, const float* H_ha
     if (!transpose) {
         if (p->m > 0 && (!H_own || !Z)) return fail(p, PGCN_ERR_INVALID, "null H_own/Z");
         if (p->h > 0 && !H_halo) return fail(p, PGCN_ERR_INVALID, "h=%d but H_halo is null", p->h);
-        return launch_spmm(p, p->fwd, H_own, H_halo, p->m, Z, nullptr, p->m, nullptr, f, 0, st);
+        return launch_spmm(p, p->fwd, H_own, H_halo, p->m, Z, nullptr, p->m, f, 0, st);
     }
     if (p->m > 0 && (!H_own || !Z)) return fail(p, PGCN_ERR_INVALID, "null gZ/G");
     if (p->h > 0 && !Z_halo) return fail(p, PGCN_ERR_INVALID, "h=%d but Z_halo is null", p->h);
-    return launch_spmm(p, p->tr, H_own, nullptr, p->m, Z, Z_halo, p->m, nullptr, f, 0, st);
+    return launch_spmm(p, p->tr, H_own, nullptr, p->m, Z, Z_halo, p->m, f, 0, st);
 }
 
 int pgcn_pack(pgcn_plan* p, const float* H, float* send_slab, int32_t f, void* stream)
@@ -757,7 +791,7 @@ int pgcn_forward(pgcn_plan* p, const float* H_own, float* Z, int32_t f, void* st
     if (p->m > 0 && (!H_own || !Z)) return fail(p, PGCN_ERR_INVALID, "null H_own/Z");
     cudaStream_t st = (cudaStream_t)stream;
     if (p->k == 1)
-        return launch_spmm(p, p->fwd, H_own, p->d_halo_slab, p->m, Z, nullptr, p->m, nullptr, f, 0, st);
+        return launch_spmm(p, p->fwd, H_own, p->d_halo_slab, p->m, Z, nullptr, p->m, f, 0, st);
 
     const bool split = p->have_split && p->opt_overlap;
     if (p->p2p && (f % 4 == 0)) {
@@ -771,12 +805,12 @@ int pgcn_forward(pgcn_plan* p, const float* H_own, float* Z, int32_t f, void* st
         if ((rc = p2p_signal_wait(p, st, true, false))) return rc;
         float* halo = arena_ptr(p->arena, p->off_fwd[par]);
         if (split) {
-            if ((rc = launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, nullptr, f, 0, st))) return rc;
+            if ((rc = launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, f, 0, st))) return rc;
             if ((rc = p2p_signal_wait(p, st, false, true))) return rc;
-            return launch_spmm(p, p->halo, H_own, halo, p->m, Z, nullptr, p->m, p->d_halo_rowmap, f, 1, st);
+            return launch_spmm(p, p->halo, H_own, halo, p->m, Z, nullptr, p->m, f, 1, st);
         }
         if ((rc = p2p_signal_wait(p, st, false, true))) return rc;
-        return launch_spmm(p, p->fwd, H_own, halo, p->m, Z, nullptr, p->m, nullptr, f, 0, st);
+        return launch_spmm(p, p->fwd, H_own, halo, p->m, Z, nullptr, p->m, f, 0, st);
     }
     if (!p->comm) return fail(p, PGCN_ERR_STATE, "k=%d: call pgcn_comm_init or pgcn_p2p_import first", p->k);
     if (split) {
@@ -786,13 +820,13 @@ int pgcn_forward(pgcn_plan* p, const float* H_own, float* Z, int32_t f, void* st
         if ((rc = launch_pack(p, H_own, p->d_send_slab, nullptr, f, p->comm_stream))) return rc;
         if ((rc = nccl_exchange(p, p->d_send_slab, p->d_halo_slab, f, 0, p->comm_stream))) return rc;
         CU(p, cudaEventRecord(p->ev_b, p->comm_stream));
-        if ((rc = launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, nullptr, f, 0, st))) return rc;
+        if ((rc = launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, f, 0, st))) return rc;
         CU(p, cudaStreamWaitEvent(st, p->ev_b, 0));
-        return launch_spmm(p, p->halo, H_own, p->d_halo_slab, p->m, Z, nullptr, p->m, p->d_halo_rowmap, f, 1, st);
+        return launch_spmm(p, p->halo, H_own, p->d_halo_slab, p->m, Z, nullptr, p->m, f, 1, st);
     }
     if ((rc = launch_pack(p, H_own, p->d_send_slab, nullptr, f, st))) return rc;
     if ((rc = nccl_exchange(p, p->d_send_slab, p->d_halo_slab, f, 0, st))) return rc;
-    return launch_spmm(p, p->fwd, H_own, p->d_halo_slab, p->m, Z, nullptr, p->m, nullptr, f, 0, st);
+    return launch_spmm(p, p->fwd, H_own, p->d_halo_slab, p->m, Z, nullptr, p->m, f, 0, st);
 }
 
 int pgcn_backward(pgcn_plan* p, const float* gZ, float* G_own, int32_t f, void* stream)
@@ -802,7 +836,7 @@ int pgcn_backward(pgcn_plan* p, const float* gZ, float* G_own, int32_t f, void* 
     if (p->m > 0 && (!gZ || !G_own)) return fail(p, PGCN_ERR_INVALID, "null gZ/G_own");
     cudaStream_t st = (cudaStream_t)stream;
     // A^T g : rows [0,m) -> G_own, rows [m,m+h) -> halo partials, already in reverse wire order
-    if ((rc = launch_spmm(p, p->tr, gZ, nullptr, p->m, G_own, p->d_hsend_slab, p->m, nullptr, f, 0, st))) return rc;
+    if ((rc = launch_spmm(p, p->tr, gZ, nullptr, p->m, G_own, p->d_hsend_slab, p->m, f, 0, st))) return rc;
     if (p->k == 1) return 0;
     if (p->p2p && (f % 4 == 0)) {
         ++p->epoch;

@@ -12,12 +12,13 @@
 // Design:
 //   * the host cuts the row range into "row blocks" of ~equal nnz; one LANE GROUP of LPE lanes
 //     (LPE = 4..32, a sub-warp for narrow feature tiles) walks one block's edge range and keeps
-//     a segmented running sum: the accumulator is flushed each time the edge index crosses a
-//     row boundary, so column indices and values are read fully coalesced (LPE at a time) no
-//     matter how short the rows are;
+//     a segmented running sum: the last entry of every row is marked in bit 31 of its column
+//     index and the accumulator is flushed when the mark is met, so column indices and values
+//     are read fully coalesced (LPE at a time) no matter how short the rows are and the kernel
+//     never touches row pointers;
 //   * each gathered H row segment is read with 16-byte loads by consecutive lanes
-//     (LPE*16 B contiguous = whole 128-B lines for LPE >= 8), U rows in flight per lane group
-//     before the first FMA consumes one (memory-level parallelism);
+//     (LPE*16 B contiguous = whole 128-B lines for LPE >= 8), in double-buffered groups of U so
+//     2U rows are in flight per lane group (memory-level parallelism);
 //   * rows longer than `long_row` are split into segments that write partial sums to a side
 //     buffer; a second tiny kernel adds the segments in a fixed order (deterministic, no atomics);
 //   * blockIdx.y walks feature tiles, so a wide H can be processed one L2-resident column slice
@@ -28,12 +29,15 @@
 
 namespace pgcn {
 
+// Bit 31 of a stored column index marks the LAST entry of its row: the kernel needs no row
+// pointers at all — it walks a block's edge range and flushes when it meets the mark.
+constexpr int kLastFlag = (int)0x80000000;
+constexpr int kColMask = 0x7fffffff;
+
 struct SpmmArgs {
-    const int4* blocks;      // {row_begin, nrows | -(slot+1), e_begin, e_end}
+    const int4* blocks;      // {first row (compact id), nrows | -(slot+1), e_begin, e_end}
     int nblocks;
-    int nrows;               // rows of the CSR being multiplied
-    const int* rowptr;       // nrows + 1
-    const int* colidx;
+    const int* colflag;      // column index | kLastFlag on the last entry of each (non-empty) row
     const float* vals;
     const float* H0;         // columns [0, split)
     const float* H1;         // columns [split, ...)   (halo slab), may be null when unused
@@ -41,7 +45,8 @@ struct SpmmArgs {
     float* Z0;               // output rows [0, zsplit)
     float* Z1;               // output rows [zsplit, ...)
     int zsplit;
-    const int* rowmap;       // optional: output row id = rowmap[row] (compact halo-part CSR)
+    const int* rowids;       // optional: compact row id -> output row (empty rows squeezed out,
+                             // or the halo-part matrix that only holds boundary rows)
     float* partial;          // side buffer for split rows, row stride f
     int f;                   // feature width == leading dimension of H0/H1/Z0/Z1/partial
     int beta;                // 0: Z = A*H ; 1: Z += A*H
@@ -74,13 +79,30 @@ __device__ __forceinline__ void st_out(float* p, const float& v) { __stcs(p, v);
 
 constexpr int kSpmmThreads = 256;
 
-// LPE lanes per edge group, VPL vectors per lane, VW floats per vector, U gathered rows in flight.
+// LPE lanes per edge group, VPL vectors per lane, VW floats per vector; gathers are issued in
+// groups of U rows and double-buffered, so up to 2U rows are in flight per lane group.
+// Occupancy target per SM: the gathers are latency-bound, so the register budget is capped to keep
+// 48-64 warps resident (2 rows in flight: 8 CTAs, 4 rows: 6 CTAs, 8 rows: 4 CTAs of 256 threads).
+#ifndef PGCN_OCC
+#define PGCN_OCC 1
+#endif
+constexpr int spmm_min_ctas(int vpl, int u)
+{
+#if PGCN_OCC == 0
+    return 1;                                   // let ptxas pick the register count
+#elif PGCN_OCC == 2
+    return (vpl * u <= 1) ? 6 : (vpl * u <= 2 ? 5 : (vpl * u <= 4 ? 3 : 2));
+#else
+    return (vpl * u <= 1) ? 8 : (vpl * u <= 2 ? 6 : (vpl * u <= 4 ? 4 : 2));
+#endif
+}
+
 template <int LPE, int VPL, int VW, int U>
-__global__ void __launch_bounds__(kSpmmThreads)
+__global__ void __launch_bounds__(kSpmmThreads, spmm_min_ctas(VPL, U))
 spmm_rowblock_kernel(const SpmmArgs a)
 {
     typedef typename Vec<VW>::type vec_t;
-    static_assert(LPE >= U && (LPE % U) == 0, "U must divide LPE");
+    static_assert(LPE % (2 * U) == 0, "2U must divide LPE");
     const int lane_w = threadIdx.x & 31;
     const int gl = threadIdx.x & (LPE - 1);
     const unsigned gmask = (LPE == 32) ? 0xffffffffu
@@ -89,8 +111,7 @@ spmm_rowblock_kernel(const SpmmArgs a)
     if (group >= a.nblocks) return;           // whole lane groups leave together
 
     const int4 b = a.blocks[group];
-    const bool seg = b.y < 0;                 // a segment of one split row
-    const int row_stop = seg ? b.x : b.x + b.y;
+    const bool seg = b.y < 0;                 // a segment of one split row: row marks are ignored
     const int e_end = b.w;
     int e = b.z;
     int row = b.x;
@@ -105,23 +126,13 @@ spmm_rowblock_kernel(const SpmmArgs a)
         fok[v] = foff[v] < a.f;               // f % VW == 0 is guaranteed by the launcher
     }
 
-    // row-end lookahead: lane i of the group caches rowptr[rbase + 1 + i]
-    int rbase = row;
-    int rp_cache = 0x7fffffff;
-    int row_end = 0x7fffffff;
-    if (!seg) {
-        const int idx = rbase + 1 + gl;
-        if (idx <= a.nrows) rp_cache = __ldg(a.rowptr + idx);
-        row_end = __shfl_sync(gmask, rp_cache, 0, LPE);
-    }
-
     vec_t acc[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) acc[v] = vzero((vec_t*)nullptr);
 
     auto flush_row = [&]() {
         // write the finished row, clear the accumulator, advance to the next row of the block
-        const int orow = a.rowmap ? __ldg(a.rowmap + row) : row;
+        const int orow = (a.rowids != nullptr) ? __ldg(a.rowids + row) : row;
         float* zrow = (orow < a.zsplit) ? a.Z0 + (size_t)orow * a.f
                                         : a.Z1 + (size_t)(orow - a.zsplit) * a.f;
 #pragma unroll
@@ -134,22 +145,14 @@ spmm_rowblock_kernel(const SpmmArgs a)
             acc[v] = vzero((vec_t*)nullptr);
         }
         ++row;
-        int kk = row - rbase;
-        if (kk == LPE) {
-            rbase = row;
-            kk = 0;
-            const int idx = rbase + 1 + gl;
-            rp_cache = (idx <= a.nrows) ? __ldg(a.rowptr + idx) : 0x7fffffff;
-        }
-        row_end = __shfl_sync(gmask, rp_cache, kk, LPE);
     };
 
-    // software pipeline: the (column, value) pair of the NEXT chunk is already in flight while the
+    // software pipeline 1: the (column, value) pair of the NEXT chunk is in flight while the
     // current chunk's rows are gathered
     int c_next = 0;
     float w_next = 0.f;
     if (e + gl < e_end) {
-        c_next = ld_stream(a.colidx + e + gl);
+        c_next = ld_stream(a.colflag + e + gl);
         w_next = ld_stream(a.vals + e + gl);
     }
     while (e < e_end) {
@@ -157,37 +160,44 @@ spmm_rowblock_kernel(const SpmmArgs a)
         const int c = c_next;
         const float w = w_next;
         if (e + LPE + gl < e_end) {
-            c_next = ld_stream(a.colidx + e + LPE + gl);
+            c_next = ld_stream(a.colflag + e + LPE + gl);
             w_next = ld_stream(a.vals + e + LPE + gl);
         }
-        // rolled on purpose: the body (U gathers, U FMAs, U flush sites) stays a few hundred SASS
-        // instructions; fully unrolled it was ~5000 and 1/3 of the issue slots stalled on no_inst
+        // software pipeline 2: two register buffers of U gathered rows; the gathers of group g+1 are
+        // issued before group g is consumed. The loop stays rolled (compact SASS: the fully unrolled
+        // first version spent 1/3 of its issue slots waiting on instruction fetch).
+        vec_t rA[U][VPL], rB[U][VPL];
+        int cA[U], cB[U];
+#define PGCN_ISSUE(R, CR, J)                                                                   \
+    _Pragma("unroll") for (int u = 0; u < U; ++u) {                                            \
+        CR[u] = __shfl_sync(gmask, c, (J) + u, LPE);                                           \
+        if ((J) + u < n) {                                                                     \
+            const int cj = CR[u] & kColMask;                                                   \
+            const float* hrow = (cj < a.split) ? a.H0 + (size_t)cj * a.f                       \
+                                               : a.H1 + (size_t)(cj - a.split) * a.f;         \
+            _Pragma("unroll") for (int v = 0; v < VPL; ++v)                                    \
+                if (fok[v]) R[u][v] = ld_feat(reinterpret_cast<const vec_t*>(hrow + foff[v])); \
+        }                                                                                      \
+    }
+#define PGCN_CONSUME(R, CR, J)                                                                 \
+    _Pragma("unroll") for (int u = 0; u < U; ++u) {                                            \
+        const float wj = __shfl_sync(gmask, w, (J) + u, LPE);                                  \
+        if ((J) + u < n) {                                                                     \
+            _Pragma("unroll") for (int v = 0; v < VPL; ++v)                                    \
+                if (fok[v]) vfma(acc[v], wj, R[u][v]);                                         \
+            if (CR[u] < 0 && !seg) flush_row();                                                \
+        }                                                                                      \
+    }
+        PGCN_ISSUE(rA, cA, 0)
 #pragma unroll 1
-        for (int j0 = 0; j0 < n; j0 += U) {
-            vec_t r[U][VPL];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int cj = __shfl_sync(gmask, c, j0 + u, LPE);
-                if (j0 + u < n) {
-                    const float* hrow = (cj < a.split) ? a.H0 + (size_t)cj * a.f
-                                                       : a.H1 + (size_t)(cj - a.split) * a.f;
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v)
-                        if (fok[v]) r[u][v] = ld_feat(reinterpret_cast<const vec_t*>(hrow + foff[v]));
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const float wj = __shfl_sync(gmask, w, j0 + u, LPE);
-                if (j0 + u < n) {
-                    const int idx = e + j0 + u;
-                    while (idx >= row_end) flush_row();      // also emits empty rows
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v)
-                        if (fok[v]) vfma(acc[v], wj, r[u][v]);
-                }
-            }
+        for (int j0 = 0; j0 < n; j0 += 2 * U) {
+            PGCN_ISSUE(rB, cB, j0 + U)
+            PGCN_CONSUME(rA, cA, j0)
+            PGCN_ISSUE(rA, cA, j0 + 2 * U)
+            PGCN_CONSUME(rB, cB, j0 + U)
         }
+#undef PGCN_ISSUE
+#undef PGCN_CONSUME
         e += n;
     }
 
@@ -196,9 +206,28 @@ spmm_rowblock_kernel(const SpmmArgs a)
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
             if (fok[v]) *reinterpret_cast<vec_t*>(prow + foff[v]) = acc[v];
-    } else {
-        while (row < row_stop) flush_row();                   // last row + trailing empty rows
     }
+}
+
+// Rows without any stored entry are squeezed out of the schedule; they are zero-filled here.
+struct ZeroArgs {
+    const int* rows; int nrows_empty;
+    float* Z0; float* Z1; int zsplit; int f;
+};
+
+template <int VW>
+__global__ void __launch_bounds__(256)
+zero_rows_kernel(const ZeroArgs a)
+{
+    typedef typename Vec<VW>::type vec_t;
+    const int nvec = a.f / VW;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)a.nrows_empty * nvec) return;
+    const int i = (int)(t / nvec);
+    const int v = (int)(t - (long long)i * nvec);
+    const int orow = __ldg(a.rows + i);
+    float* zrow = (orow < a.zsplit) ? a.Z0 + (size_t)orow * a.f : a.Z1 + (size_t)(orow - a.zsplit) * a.f;
+    reinterpret_cast<vec_t*>(zrow)[v] = vzero((vec_t*)nullptr);
 }
 
 // Z[row] (+)= sum of the row's segments, in segment order. One thread per (split row, vector).
@@ -207,7 +236,7 @@ struct FixupArgs {
     int nlong;
     const float* partial;
     float* Z0; float* Z1; int zsplit;
-    const int* rowmap;
+    const int* rowids;
     int f; int beta;
 };
 
@@ -222,7 +251,7 @@ spmm_fixup_kernel(const FixupArgs a)
     const int lr = (int)(t / nvec);
     const int v = (int)(t - (long long)lr * nvec);
     const int4 d = a.long_rows[lr];
-    const int orow = a.rowmap ? __ldg(a.rowmap + d.x) : d.x;
+    const int orow = a.rowids ? __ldg(a.rowids + d.x) : d.x;
     float* zrow = (orow < a.zsplit) ? a.Z0 + (size_t)orow * a.f : a.Z1 + (size_t)(orow - a.zsplit) * a.f;
     vec_t* zp = reinterpret_cast<vec_t*>(zrow) + v;
     vec_t s = vzero((vec_t*)nullptr);

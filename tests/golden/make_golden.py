@@ -38,6 +38,7 @@ from scipy.io import mmread
 
 REF = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 SEED = 20260922
 
 
@@ -159,26 +160,37 @@ def main():
         ("karate_k3_stchp", kar, kst, 3, 20),
     ]
     for tag, path, pv, k, f in cases:
-        run_case(tag, path, pv, k, f, port)
+        if "--e2e-only" not in sys.argv:
+            run_case(tag, path, pv, k, f, port)
         port += 1
 
-    # end-to-end stdout of the reference's own run(): gemat11, shipped .3.hp, -l 2 -f 16, gloo
-    k, L, f = 3, 2, 16
-    mp.spawn(e2e_worker, args=(k, port, gem, os.path.join(REF, "GPU/hypergraph/data/gemat11.mtx.3.hp"), L, f, HERE),
-             nprocs=k, join=True)
-    txt = open(os.path.join(HERE, "_tmp_e2e_r0.txt")).read()
-    for r in range(k):
-        os.remove(os.path.join(HERE, "_tmp_e2e_r%d.txt" % r))
-    rec = {"cmd": "PGCN.py -a gemat11.mtx -p gemat11.mtx.3.hp -b gloo -s 3 -l 2 -f 16 (torch.manual_seed(1000+rank))",
-           "losses": [], "total_vol": None, "total_nmsg": None}
-    for line in txt.splitlines():
-        if line.startswith("Epoch"):
-            rec["losses"].append(float(line.split("Loss")[1]))
-        if line.startswith("total_vol"):
-            parts = line.replace(":", " ").split()
-            rec["total_vol"], rec["total_nmsg"] = int(parts[1]), int(parts[3])
-    json.dump(rec, open(os.path.join(HERE, "gemat11_k3_hp_e2e.json"), "w"), indent=1)
-    print(rec)
+    # end-to-end stdout of the reference's own run(): gemat11, -l 2 -f 16, gloo, k = 1, 2, 3
+    # (k = 3 uses the shipped .3.hp; k = 2 merges its parts 1 and 2; k = 1 is all zeros)
+    import tempfile
+    from pgcn_b200 import graphio
+    L, f = 2, 16
+    allrec = {}
+    for k, pv in ((1, [0] * len(hp3)), (2, [min(p, 1) for p in hp3]), (3, hp3)):
+        port += 1
+        with tempfile.TemporaryDirectory() as td:
+            pv_path = os.path.join(td, "gemat11.mtx.%d.hp" % k)
+            graphio.write_partvec(pv_path, pv)
+            mp.spawn(e2e_worker, args=(k, port, gem, pv_path, L, f, HERE), nprocs=k, join=True)
+        txt = open(os.path.join(HERE, "_tmp_e2e_r0.txt")).read()
+        for r in range(k):
+            os.remove(os.path.join(HERE, "_tmp_e2e_r%d.txt" % r))
+        rec = {"cmd": "PGCN.py -a gemat11.mtx -p <partvec k=%d> -b gloo -s %d -l 2 -f 16 (torch.manual_seed(1000+rank))" % (k, k),
+               "losses": [], "total_vol": None, "total_nmsg": None}
+        for line in txt.splitlines():
+            if line.startswith("Epoch"):
+                rec["losses"].append(float(line.split("Loss")[1]))
+            if line.startswith("total_vol"):
+                parts = line.replace(":", " ").split()
+                rec["total_vol"], rec["total_nmsg"] = int(parts[1]), int(parts[3])
+        allrec["k%d" % k] = rec
+        print(k, rec)
+    json.dump(allrec, open(os.path.join(HERE, "gemat11_e2e.json"), "w"), indent=1)
+    json.dump(allrec["k3"], open(os.path.join(HERE, "gemat11_k3_hp_e2e.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -69,17 +69,19 @@ def main():
         # n rows, degree d, columns uniform in a window of W rows: working set W*f*4 bytes
         n, d, f = 1_000_000, 16, 128
         rng = np.random.default_rng(0)
-        for W in (32_000, 64_000, 96_000, 128_000, 192_000, 256_000, 384_000, 512_000, 1_000_000):
+        windows = (32_000, 1_000_000) if args.iters <= 3 else (32_000, 64_000, 96_000, 128_000, 192_000, 256_000, 384_000, 512_000, 1_000_000)
+        for W in windows:
             col = rng.integers(0, W, size=n * d, dtype=np.int64)
             row = np.repeat(np.arange(n, dtype=np.int64), d)
             A = sp.coo_matrix((np.ones(n * d, dtype=np.float32), (row, col)), shape=(n, n))
             p = planmod.build_plan(A, np.zeros(n, dtype=np.int64), 0, 1, f, device=dev)
             H = torch.rand((n, f), device=dev); Z = torch.empty((n, f), device=dev)
-            for tile in (0, 32):
+            for tile, unroll in ((0, 2), (0, 4), (0, 8), (32, 4)):
                 p.set_option("tile_floats", tile)
+                p.set_option("unroll", unroll)
                 med, mn = timed(lambda: cabi.check(lib.pgcn_spmm(p.handle, 0, H.data_ptr(), None, Z.data_ptr(), None, f, stream), p.handle), args.iters)
                 nnz = p.lp.nnz()
-                emit({"probe": "gather", "window_rows": W, "window_MB": W * f * 4 / 1e6, "tile_floats": tile, "ms": med,
+                emit({"probe": "gather", "window_rows": W, "window_MB": W * f * 4 / 1e6, "tile_floats": tile, "unroll": unroll, "ms": med,
                       "gather_GBs": nnz * f * 4 / med / 1e6, "edges_per_s": nnz / med * 1e3})
             p.close()
         return
@@ -118,6 +120,9 @@ def main():
     elif args.sweep == "default":
         for epb, tile, unroll in itertools.product((64, 128, 256, 512), (0, 64, 32, 16), (2, 4, 8)):
             point({"edges_per_block": epb, "tile_floats": tile, "unroll": unroll})
+    elif args.sweep == "small":
+        for epb, unroll in itertools.product((96, 128, 192, 256), (2, 4, 8)):
+            point({"edges_per_block": epb, "tile_floats": 0, "unroll": unroll})
     elif args.sweep == "fine":
         for epb, tile, lr in itertools.product((96, 128, 192, 256, 384), (0, 64, 32), (0, 256, 1024, 4096)):
             point({"edges_per_block": epb, "tile_floats": tile, "long_row": lr})
