@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -121,7 +122,7 @@ struct pgcn_plan {
     float* d_hsend_slab = nullptr;   // h x f_max   (reverse send: halo partials of A^T g)
 
     // options
-    int64_t opt_epb = 256, opt_long = 0, opt_tile = 0, opt_unroll = 0, opt_overlap = 1;
+    int64_t opt_epb = 128, opt_long = 0, opt_tile = 0, opt_unroll = 0, opt_overlap = 1, opt_hot_mb = 64;
 
     // NCCL
     ncclComm_t comm = nullptr;
@@ -184,12 +185,23 @@ int upload(pgcn_plan* p, T** dst, const T* src, size_t n)
 // Upload one CSR. Rows without entries are squeezed out of the walked row space (their outputs are
 // zero-filled by a separate launch); `ext_rowmap` maps the rows of an already-compact matrix (the
 // halo-column part, which only holds boundary rows) to output rows.
+// `col_refs[j]` = number of stored entries in column j (null: no hot/cold marking): columns are
+// ranked by it and only as many of the most-referenced rows of H as fit `hot_rows` stay unmarked;
+// every other column gets kColdFlag and is gathered with an L2 evict_first policy.
 int csr_upload(pgcn_plan* p, DevCsr& c, int nrows, const int* rowptr, const int* colidx, const float* vals,
-               const std::vector<int>* ext_rowmap = nullptr)
+               const std::vector<int>* ext_rowmap = nullptr, const int* col_refs = nullptr, int ncols = 0,
+               int64_t hot_rows = 0)
 {
     c.nrows = nrows;
     c.nnz = rowptr[nrows];
     std::vector<int> colflag(colidx, colidx + c.nnz);
+    if (col_refs && ncols > hot_rows && hot_rows > 0) {
+        std::vector<int> sorted(col_refs, col_refs + ncols);
+        std::nth_element(sorted.begin(), sorted.begin() + (ncols - hot_rows), sorted.end());
+        const int thresh = sorted[ncols - hot_rows];          // columns with refs <= thresh are cold
+        for (int64_t e = 0; e < c.nnz; ++e)
+            if (col_refs[colidx[e]] <= thresh) colflag[e] |= kColdFlag;
+    }
     std::vector<int> rowids, empty;
     c.h_rowptr.clear();
     c.h_rowptr.push_back(0);
@@ -300,7 +312,7 @@ TileCfg choose_tile(const pgcn_plan* p, int f)
     t.tiles = (nvec + t.lpe * t.vpl - 1) / (t.lpe * t.vpl);
     // `unroll` = rows in flight per lane group = 2U (two register buffers of U rows)
     int u = (int)p->opt_unroll / 2;
-    if (u != 1 && u != 2 && u != 4) u = (t.vpl >= 4) ? 1 : 2;
+    if (u != 1 && u != 2 && u != 4) u = 1;      // measured: 2 rows in flight x 48 warps/SM beats deeper pipelines
     if (t.vw == 1) u = 2;
     t.u = std::min(u, t.lpe / 2);
     return t;
@@ -498,6 +510,7 @@ int pgcn_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* 
     if (!out) return fail(nullptr, PGCN_ERR_INVALID, "out is null");
     *out = nullptr;
     if (!rowptr || !t_rowptr || !send_off || !recv_off) return fail(nullptr, PGCN_ERR_INVALID, "null index array");
+    if ((int64_t)m + h >= (int64_t)kColMask) return fail(nullptr, PGCN_ERR_INVALID, "m + h must be below 2^30");
     if (m < 0 || h < 0 || k < 1 || rank < 0 || rank >= k || f_max < 1)
         return fail(nullptr, PGCN_ERR_INVALID, "bad sizes m=%d h=%d k=%d rank=%d f_max=%d", m, h, k, rank, f_max);
     if (recv_off[k] != h) return fail(nullptr, PGCN_ERR_INVALID, "recv_off[k]=%lld != h=%d", (long long)recv_off[k], h);
@@ -524,8 +537,15 @@ int pgcn_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* 
     cudaGetDevice(&p->device);
 
 #define TRY(expr) do { int rc__ = (expr); if (rc__) { g_lib_error = p->err; pgcn_plan_destroy(p); return rc__; } } while (0)
-    TRY(csr_upload(p, p->fwd, m, rowptr, colidx, vals));
-    TRY(csr_upload(p, p->tr, m + h, t_rowptr, t_colidx, t_vals));
+    // column reference counts: forward columns = rows of the transpose and vice versa
+    std::vector<int> refs_fwd((size_t)m + h), refs_tr((size_t)m);
+    for (int r = 0; r < m + h; ++r) refs_fwd[r] = t_rowptr[r + 1] - t_rowptr[r];
+    for (int r = 0; r < m; ++r) refs_tr[r] = rowptr[r + 1] - rowptr[r];
+    // rows of H kept hot in L2: about half of the 126 MB L2, the rest is left to the streams
+    if (const char* e = getenv("PGCN_HOT_MB")) p->opt_hot_mb = std::max<long long>(0, atoll(e));   // tuning knob
+    const int64_t hot_rows = std::max<int64_t>(1, (p->opt_hot_mb << 20) / ((int64_t)f_max * 4));
+    TRY(csr_upload(p, p->fwd, m, rowptr, colidx, vals, nullptr, refs_fwd.data(), m + h, hot_rows));
+    TRY(csr_upload(p, p->tr, m + h, t_rowptr, t_colidx, t_vals, nullptr, refs_tr.data(), m, hot_rows));
 
     // distinct referenced columns / transposed rows (for the roofline's compulsory bytes)
     for (int r = 0; r < m + h; ++r) if (t_rowptr[r + 1] > t_rowptr[r]) ++p->cols_ref;
@@ -546,8 +566,8 @@ int pgcn_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* 
             o_rp[r + 1] = (int)o_ci.size();
             if (h_ci.size() > before) { h_map.push_back(r); h_rp.push_back((int)h_ci.size()); }
         }
-        TRY(csr_upload(p, p->own, m, o_rp.data(), o_ci.data(), o_v.data()));
-        TRY(csr_upload(p, p->halo, (int)h_map.size(), h_rp.data(), h_ci.data(), h_v.data(), &h_map));
+        TRY(csr_upload(p, p->own, m, o_rp.data(), o_ci.data(), o_v.data(), nullptr, refs_fwd.data(), m + h, hot_rows));
+        TRY(csr_upload(p, p->halo, (int)h_map.size(), h_rp.data(), h_ci.data(), h_v.data(), &h_map, refs_fwd.data(), m + h, hot_rows));
         p->have_split = true;
     }
 

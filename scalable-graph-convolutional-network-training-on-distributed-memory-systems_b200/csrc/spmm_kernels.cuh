@@ -31,8 +31,16 @@ namespace pgcn {
 
 // Bit 31 of a stored column index marks the LAST entry of its row: the kernel needs no row
 // pointers at all — it walks a block's edge range and flushes when it meets the mark.
+// Bit 30 marks a COLD column (few references): its H row is loaded with an L2 evict_first policy
+// while the hot rows (hubs, the part of H that fits in L2) are loaded evict_last, so streaming
+// traffic does not push the re-used rows out of the 126 MB L2.
 constexpr int kLastFlag = (int)0x80000000;
-constexpr int kColMask = 0x7fffffff;
+constexpr int kColdFlag = 0x40000000;
+constexpr int kColMask = 0x3fffffff;
+
+#ifndef PGCN_LDMODE
+#define PGCN_LDMODE 0      // 0: ld.global.nc   1: + L1::no_allocate   2: L2 hot/cold hints   3: 2 + L1::no_allocate
+#endif
 
 struct SpmmArgs {
     const int4* blocks;      // {first row (compact id), nrows | -(slot+1), e_begin, e_end}
@@ -70,6 +78,43 @@ __device__ __forceinline__ void vadd(float& a, const float& r) { a += r; }
 // H rows: read-only path, default L1/L2 allocation (hub rows are re-used).
 __device__ __forceinline__ float4 ld_feat(const float4* p) { return __ldg(p); }
 __device__ __forceinline__ float ld_feat(const float* p) { return __ldg(p); }
+
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// gather of one H-row vector with an explicit L2 eviction policy
+__device__ __forceinline__ float4 ld_feat_hint(const float4* p, unsigned long long pol) {
+    float4 r;
+#if PGCN_LDMODE == 3
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+#elif PGCN_LDMODE == 2
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+#elif PGCN_LDMODE == 1
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+#else
+    r = __ldg(p);
+#endif
+    return r;
+}
+__device__ __forceinline__ float ld_feat_hint(const float* p, unsigned long long pol) {
+    float r;
+#if PGCN_LDMODE >= 2
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+#else
+    r = __ldg(p);
+#endif
+    return r;
+}
 // column indices / values: touched once -> streaming, do not displace H rows.
 __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
@@ -84,7 +129,7 @@ constexpr int kSpmmThreads = 256;
 // Occupancy target per SM: the gathers are latency-bound, so the register budget is capped to keep
 // 48-64 warps resident (2 rows in flight: 8 CTAs, 4 rows: 6 CTAs, 8 rows: 4 CTAs of 256 threads).
 #ifndef PGCN_OCC
-#define PGCN_OCC 1
+#define PGCN_OCC 2
 #endif
 constexpr int spmm_min_ctas(int vpl, int u)
 {
@@ -125,6 +170,9 @@ spmm_rowblock_kernel(const SpmmArgs a)
         foff[v] = fbase + (v * LPE + gl) * VW;
         fok[v] = foff[v] < a.f;               // f % VW == 0 is guaranteed by the launcher
     }
+
+    const unsigned long long pol_hot = l2_policy_evict_last();
+    const unsigned long long pol_cold = l2_policy_evict_first();
 
     vec_t acc[VPL];
 #pragma unroll
@@ -173,10 +221,11 @@ spmm_rowblock_kernel(const SpmmArgs a)
         CR[u] = __shfl_sync(gmask, c, (J) + u, LPE);                                           \
         if ((J) + u < n) {                                                                     \
             const int cj = CR[u] & kColMask;                                                   \
+            const unsigned long long pol = (CR[u] & kColdFlag) ? pol_cold : pol_hot;           \
             const float* hrow = (cj < a.split) ? a.H0 + (size_t)cj * a.f                       \
                                                : a.H1 + (size_t)(cj - a.split) * a.f;         \
             _Pragma("unroll") for (int v = 0; v < VPL; ++v)                                    \
-                if (fok[v]) R[u][v] = ld_feat(reinterpret_cast<const vec_t*>(hrow + foff[v])); \
+                if (fok[v]) R[u][v] = ld_feat_hint(reinterpret_cast<const vec_t*>(hrow + foff[v]), pol); \
         }                                                                                      \
     }
 #define PGCN_CONSUME(R, CR, J)                                                                 \

@@ -120,6 +120,9 @@ def main():
     elif args.sweep == "default":
         for epb, tile, unroll in itertools.product((64, 128, 256, 512), (0, 64, 32, 16), (2, 4, 8)):
             point({"edges_per_block": epb, "tile_floats": tile, "unroll": unroll})
+    elif args.sweep == "mini":
+        for epb, unroll in itertools.product((128, 160), (2, 4)):
+            point({"edges_per_block": epb, "tile_floats": 0, "unroll": unroll})
     elif args.sweep == "small":
         for epb, unroll in itertools.product((96, 128, 192, 256), (2, 4, 8)):
             point({"edges_per_block": epb, "tile_floats": 0, "unroll": unroll})
