@@ -135,6 +135,9 @@ def cpu_baseline(lp, f, budget_s=20.0):
     H = rng.uniform(-1, 1, size=(lp.m + lp.h, f)).astype(np.float32)
     out = np.empty((lp.m, f), dtype=np.float32)
     build_oracle.spmm_csr(lp.rowptr, lp.colidx, lp.vals, H, lp.m, out=out)       # warm-up / page-in
+    ncpu = os.cpu_count() or 1
+    build_oracle.best_thread_count(lambda: build_oracle.spmm_csr(lp.rowptr, lp.colidx, lp.vals, H, lp.m, out=out),
+                                   sorted({ncpu, max(1, ncpu // 2)}))
     times = []
     t_all = time.perf_counter()
     while len(times) < 3 or (time.perf_counter() - t_all < budget_s and len(times) < 50):
@@ -161,6 +164,9 @@ def run_reference(args):
     rng = np.random.RandomState(1)
     H = rng.uniform(-1, 1, size=(n, f)).astype(np.float32)
     out = np.empty((n, f), dtype=np.float32)
+    ncpu = os.cpu_count() or 1
+    build_oracle.best_thread_count(lambda: build_oracle.spmm_csr(lp.rowptr, lp.colidx, lp.vals, H, n, out=out),
+                                   sorted({ncpu, max(1, ncpu // 2)}))
     for _ in range(max(args.warmup, 1)):
         build_oracle.spmm_csr(lp.rowptr, lp.colidx, lp.vals, H, n, out=out)
     t0 = time.perf_counter()
@@ -329,7 +335,7 @@ def main():
                 "workload": "%s: R-MAT %d vertices / %d edges (+%d self loops after A+I), f=%d, one forward aggregation "
                             "(halo exchange + Z=A_local*H) per step" % (args.config, n, nnz, n, f),
                 "partition": pv_name, "transport": transport, "l2": "inputs larger than L2 (H and Z %.0f MB each per rank)" % (lp.m * f * 4 / 1e6),
-                "plan_options": {k_: plan.get_option(k_) for k_ in ("edges_per_block", "long_row", "tile_floats", "unroll", "overlap")},
+                "plan_options": {k_: plan.get_option(k_) for k_ in ("edges_per_block", "long_row", "tile_floats", "overlap")},
                 "nnz": nnz_total, "halo_rows_rank0": int(lp.h), "send_rows_rank0": int(lp.S),
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -96,10 +96,9 @@ int pgcn_plan_destroy(pgcn_plan* plan);
 
 /*
  * Scheduling tunables (take effect at the next compute call). Names:
- *   "edges_per_block"  target nnz handled by one lane group              (default 256)
+ *   "edges_per_block"  target nnz handled by one lane group              (default 128)
  *   "long_row"         rows with more nnz than this are split            (default 4*edges_per_block)
  *   "tile_floats"      feature-tile width in floats, 0 = whole row       (default 0)
- *   "unroll"           gathered rows in flight per lane group: 2, 4, 8   (default 0 = auto)
  *   "overlap"          1 = split A_local into own/halo column parts and overlap the exchange
  *                      with the own part (Parallel-GCN/main.c:271 then :295)   (default 1)
  * Split rows are always reduced in a fixed order: results are run-to-run deterministic.

@@ -35,6 +35,8 @@ def load():
         lib.spmm_csr_fp32.argtypes = [i64, vp, vp, vp, vp, i64, vp]
         lib.spmm_csr_fp32.restype = None
         lib.oracle_num_threads.restype = C.c_int
+        lib.oracle_set_threads.argtypes = [C.c_int]
+        lib.oracle_set_threads.restype = None
         _lib = lib
     return _lib
 
@@ -66,6 +68,25 @@ def spmm_csr(rowptr, colidx, vals, H, m, out=None):
 
 def num_threads():
     return int(load().oracle_num_threads())
+
+
+def set_threads(n):
+    load().oracle_set_threads(int(n))
+
+
+def best_thread_count(fn, candidates):
+    """Time `fn` once per candidate thread count and keep the fastest (SMT siblings often hurt a
+    bandwidth-bound loop): the CPU baseline is reported at its best configuration."""
+    import time
+    best, best_t = None, None
+    for c in candidates:
+        set_threads(c)
+        fn()
+        t0 = time.perf_counter(); fn(); t = time.perf_counter() - t0
+        if best_t is None or t < best_t:
+            best, best_t = c, t
+    set_threads(best)
+    return best
 
 
 if __name__ == "__main__":

@@ -73,6 +73,15 @@ void spmm_csr_fp32(int64_t m, const int32_t* rowptr, const int32_t* colidx, cons
     }
 }
 
+void oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

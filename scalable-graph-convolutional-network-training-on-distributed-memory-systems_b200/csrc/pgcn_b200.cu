@@ -122,7 +122,7 @@ struct pgcn_plan {
     float* d_hsend_slab = nullptr;   // h x f_max   (reverse send: halo partials of A^T g)
 
     // options
-    int64_t opt_epb = 128, opt_long = 0, opt_tile = 0, opt_unroll = 0, opt_overlap = 1, opt_hot_mb = 64;
+    int64_t opt_epb = 128, opt_long = 0, opt_tile = 0, opt_overlap = 1, opt_hot_mb = 64;
 
     // NCCL
     ncclComm_t comm = nullptr;
@@ -294,7 +294,7 @@ int build_schedule(pgcn_plan* p, DevCsr& c)
 
 // ---- kernel dispatch ---------------------------------------------------------------------
 
-struct TileCfg { int lpe, vpl, vw, u, tiles; };
+struct TileCfg { int lpe, vpl, vw, tiles; };
 
 int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
@@ -310,45 +310,29 @@ TileCfg choose_tile(const pgcn_plan* p, int f)
     int vpl = (tile_vecs + t.lpe - 1) / t.lpe;
     t.vpl = vpl <= 1 ? 1 : (vpl <= 2 ? 2 : 4);
     t.tiles = (nvec + t.lpe * t.vpl - 1) / (t.lpe * t.vpl);
-    // `unroll` = rows in flight per lane group = 2U (two register buffers of U rows)
-    int u = (int)p->opt_unroll / 2;
-    if (u != 1 && u != 2 && u != 4) u = 1;      // measured: 2 rows in flight x 48 warps/SM beats deeper pipelines
-    if (t.vw == 1) u = 2;
-    t.u = std::min(u, t.lpe / 2);
     return t;
 }
 
 typedef void (*spmm_fn)(const SpmmArgs);
 
-template <int LPE, int VPL, int VW>
-spmm_fn pick_u(int u)
-{
-    if (VW == 1) return spmm_rowblock_kernel<LPE, VPL, VW, 2>;
-    switch (u) {
-        case 1: return spmm_rowblock_kernel<LPE, VPL, VW, 1>;
-        case 4: return spmm_rowblock_kernel<LPE, VPL, VW, (LPE >= 8 ? 4 : 2)>;
-        default: return spmm_rowblock_kernel<LPE, VPL, VW, 2>;
-    }
-}
-
 template <int LPE, int VW>
-spmm_fn pick_vpl(int vpl, int u)
+spmm_fn pick_vpl(int vpl, bool halo)
 {
     switch (vpl) {
-        case 1: return pick_u<LPE, 1, VW>(u);
-        case 2: return pick_u<LPE, 2, VW>(u);
-        default: return pick_u<LPE, 4, VW>(u);
+        case 1: return halo ? spmm_rowblock_kernel<LPE, 1, VW, true> : spmm_rowblock_kernel<LPE, 1, VW, false>;
+        case 2: return halo ? spmm_rowblock_kernel<LPE, 2, VW, true> : spmm_rowblock_kernel<LPE, 2, VW, false>;
+        default: return halo ? spmm_rowblock_kernel<LPE, 4, VW, true> : spmm_rowblock_kernel<LPE, 4, VW, false>;
     }
 }
 
 template <int VW>
-spmm_fn pick_lpe(int lpe, int vpl, int u)
+spmm_fn pick_lpe(int lpe, int vpl, bool halo)
 {
     switch (lpe) {
-        case 4: return pick_vpl<4, VW>(vpl, u);
-        case 8: return pick_vpl<8, VW>(vpl, u);
-        case 16: return pick_vpl<16, VW>(vpl, u);
-        default: return pick_vpl<32, VW>(vpl, u);
+        case 4: return pick_vpl<4, VW>(vpl, halo);
+        case 8: return pick_vpl<8, VW>(vpl, halo);
+        case 16: return pick_vpl<16, VW>(vpl, halo);
+        default: return pick_vpl<32, VW>(vpl, halo);
     }
 }
 
@@ -378,7 +362,8 @@ int launch_spmm(pgcn_plan* p, DevCsr& c, const float* H0, const float* H1, int s
     if (c.nblocks > 0) {
         const int groups_per_cta = kSpmmThreads / t.lpe;
         dim3 grid((unsigned)((c.nblocks + groups_per_cta - 1) / groups_per_cta), (unsigned)t.tiles);
-        spmm_fn fn = (t.vw == 4) ? pick_lpe<4>(t.lpe, t.vpl, t.u) : pick_lpe<1>(t.lpe, t.vpl, t.u);
+        const bool halo = (H1 != nullptr);
+        spmm_fn fn = (t.vw == 4) ? pick_lpe<4>(t.lpe, t.vpl, halo) : pick_lpe<1>(t.lpe, t.vpl, halo);
         fn<<<grid, kSpmmThreads, 0, st>>>(a);
         ++p->launches;
     }
@@ -641,7 +626,7 @@ int pgcn_plan_set_option(pgcn_plan* p, const char* name, int64_t value)
     if (n == "edges_per_block") p->opt_epb = value;
     else if (n == "long_row") p->opt_long = value;
     else if (n == "tile_floats") p->opt_tile = value;
-    else if (n == "unroll") p->opt_unroll = value;
+    else if (n == "hot_mb") p->opt_hot_mb = value;
     else if (n == "overlap") p->opt_overlap = value;
     else return fail(p, PGCN_ERR_INVALID, "unknown option '%s'", name);
     return 0;
@@ -654,7 +639,7 @@ int64_t pgcn_plan_get_option(const pgcn_plan* p, const char* name)
     if (n == "edges_per_block") return p->opt_epb;
     if (n == "long_row") return p->opt_long;
     if (n == "tile_floats") return p->opt_tile;
-    if (n == "unroll") return p->opt_unroll;
+    if (n == "hot_mb") return p->opt_hot_mb;
     if (n == "overlap") return p->opt_overlap;
     if (n == "p2p") return p->p2p ? 1 : 0;
     if (n == "nccl") return p->comm ? 1 : 0;
@@ -821,15 +806,22 @@ int pgcn_forward(pgcn_plan* p, const float* H_own, float* Z, int32_t f, void* st
         float* dst[kMaxPeers];
         for (int q = 0; q < p->k; ++q)
             dst[q] = arena_ptr(p->peer_arena[q], p->peer_blob[q].off_fwd[par]) + (size_t)p->peer_blob[q].recv_off[p->rank] * f;
-        if ((rc = launch_pack(p, H_own, nullptr, dst, f, st))) return rc;
-        if ((rc = p2p_signal_wait(p, st, true, false))) return rc;
         float* halo = arena_ptr(p->arena, p->off_fwd[par]);
         if (split) {
+            // side stream: rows leave for the neighbours' slabs (NVLink-bound) ; main stream: own-columns SpMM.
+            // The neighbours' rows land in MY slab meanwhile; the wait kernel joins on their epoch flags.
+            CU(p, cudaEventRecord(p->ev_a, st));
+            CU(p, cudaStreamWaitEvent(p->comm_stream, p->ev_a, 0));
+            if ((rc = launch_pack(p, H_own, nullptr, dst, f, p->comm_stream))) return rc;
+            if ((rc = p2p_signal_wait(p, p->comm_stream, true, false))) return rc;
+            CU(p, cudaEventRecord(p->ev_b, p->comm_stream));
             if ((rc = launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, f, 0, st))) return rc;
             if ((rc = p2p_signal_wait(p, st, false, true))) return rc;
+            CU(p, cudaStreamWaitEvent(st, p->ev_b, 0));          // H_own is free for the caller after this
             return launch_spmm(p, p->halo, H_own, halo, p->m, Z, nullptr, p->m, f, 1, st);
         }
-        if ((rc = p2p_signal_wait(p, st, false, true))) return rc;
+        if ((rc = launch_pack(p, H_own, nullptr, dst, f, st))) return rc;
+        if ((rc = p2p_signal_wait(p, st, true, true))) return rc;
         return launch_spmm(p, p->fwd, H_own, halo, p->m, Z, nullptr, p->m, f, 0, st);
     }
     if (!p->comm) return fail(p, PGCN_ERR_STATE, "k=%d: call pgcn_comm_init or pgcn_p2p_import first", p->k);

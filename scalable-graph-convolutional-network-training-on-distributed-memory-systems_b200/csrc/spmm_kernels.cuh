@@ -17,8 +17,8 @@
 //     are read fully coalesced (LPE at a time) no matter how short the rows are and the kernel
 //     never touches row pointers;
 //   * each gathered H row segment is read with 16-byte loads by consecutive lanes
-//     (LPE*16 B contiguous = whole 128-B lines for LPE >= 8), in double-buffered groups of U so
-//     2U rows are in flight per lane group (memory-level parallelism);
+//     (LPE*16 B contiguous = whole 128-B lines for LPE >= 8), two rows in flight per lane group
+//     (register double buffer) times ~48 resident warps per SM;
 //   * rows longer than `long_row` are split into segments that write partial sums to a side
 //     buffer; a second tiny kernel adds the segments in a fixed order (deterministic, no atomics);
 //   * blockIdx.y walks feature tiles, so a wide H can be processed one L2-resident column slice
@@ -126,30 +126,42 @@ constexpr int kSpmmThreads = 256;
 
 // LPE lanes per edge group, VPL vectors per lane, VW floats per vector; gathers are issued in
 // groups of U rows and double-buffered, so up to 2U rows are in flight per lane group.
-// Occupancy target per SM: the gathers are latency-bound, so the register budget is capped to keep
-// 48-64 warps resident (2 rows in flight: 8 CTAs, 4 rows: 6 CTAs, 8 rows: 4 CTAs of 256 threads).
+// Occupancy target: the gathers are latency-bound and 2 rows in flight per lane group with ~48
+// resident warps per SM measured best (deeper per-warp pipelines only cost registers), so the
+// register budget is capped to keep 6 CTAs of 256 threads per SM for the one-vector-per-lane case.
 #ifndef PGCN_OCC
 #define PGCN_OCC 2
 #endif
-constexpr int spmm_min_ctas(int vpl, int u)
+constexpr int spmm_min_ctas(int vpl)
 {
 #if PGCN_OCC == 0
     return 1;                                   // let ptxas pick the register count
-#elif PGCN_OCC == 2
-    return (vpl * u <= 1) ? 6 : (vpl * u <= 2 ? 5 : (vpl * u <= 4 ? 3 : 2));
+#elif PGCN_OCC == 1
+    return vpl <= 1 ? 8 : (vpl <= 2 ? 6 : 4);
 #else
-    return (vpl * u <= 1) ? 8 : (vpl * u <= 2 ? 6 : (vpl * u <= 4 ? 4 : 2));
+    return vpl <= 1 ? 6 : (vpl <= 2 ? 5 : 3);
 #endif
 }
 
-template <int LPE, int VPL, int VW, int U>
-__global__ void __launch_bounds__(kSpmmThreads, spmm_min_ctas(VPL, U))
+// LPE lanes per edge group, VPL vectors per lane, VW floats per vector, HALO: columns >= split
+// live in a second base pointer (the halo slab).
+//
+// Per chunk of LPE edges a lane group stages its (column|flags, value) pairs in shared memory, so
+// the inner loop costs one broadcast LDS.64 per edge instead of two divergence-guarded shuffles;
+// the H row address is one IMAD.WIDE.U32 (32-bit column x row pitch in bytes + 64-bit base); the
+// own/halo base is a select, not a branch; full chunks run a predicate-free loop. Two gathers are in
+// flight per lane group (register double buffer A/B); the next chunk's index pairs are already in
+// flight in registers while the current chunk is processed.
+template <int LPE, int VPL, int VW, bool HALO>
+__global__ void __launch_bounds__(kSpmmThreads, spmm_min_ctas(VPL))
 spmm_rowblock_kernel(const SpmmArgs a)
 {
     typedef typename Vec<VW>::type vec_t;
-    static_assert(LPE % (2 * U) == 0, "2U must divide LPE");
+    __shared__ int2 s_cw[2][kSpmmThreads];
+
     const int lane_w = threadIdx.x & 31;
     const int gl = threadIdx.x & (LPE - 1);
+    const int gbase = threadIdx.x & ~(LPE - 1);
     const unsigned gmask = (LPE == 32) ? 0xffffffffu
                                        : (((1u << (LPE & 31)) - 1u) << (lane_w & ~(LPE - 1)));
     const int group = (int)((blockIdx.x * (unsigned)kSpmmThreads + threadIdx.x) / LPE);
@@ -157,22 +169,25 @@ spmm_rowblock_kernel(const SpmmArgs a)
 
     const int4 b = a.blocks[group];
     const bool seg = b.y < 0;                 // a segment of one split row: row marks are ignored
+    const int lastmask = seg ? 0 : kLastFlag;
     const int e_end = b.w;
     int e = b.z;
     int row = b.x;
 
-    // feature tile of this CTA column
-    const int fbase = blockIdx.y * (LPE * VPL * VW);
-    int foff[VPL];
+    // this lane's slice of a feature row: byte offset of its first vector inside the row
+    const unsigned pitch = (unsigned)a.f * 4u;                       // row pitch in bytes
+    const int f0 = blockIdx.y * (LPE * VPL * VW) + gl * VW;          // first float of vector 0
     bool fok[VPL];
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-        foff[v] = fbase + (v * LPE + gl) * VW;
-        fok[v] = foff[v] < a.f;               // f % VW == 0 is guaranteed by the launcher
-    }
+    for (int v = 0; v < VPL; ++v) fok[v] = f0 + v * LPE * VW < a.f;  // f % VW == 0 (launcher)
+    const char* hb0 = reinterpret_cast<const char*>(a.H0) + (size_t)f0 * 4;
+    const char* hb1 = HALO ? reinterpret_cast<const char*>(a.H1) + (size_t)f0 * 4 - (size_t)a.split * pitch
+                           : hb0;
 
+#if PGCN_LDMODE >= 2
     const unsigned long long pol_hot = l2_policy_evict_last();
     const unsigned long long pol_cold = l2_policy_evict_first();
+#endif
 
     vec_t acc[VPL];
 #pragma unroll
@@ -181,12 +196,14 @@ spmm_rowblock_kernel(const SpmmArgs a)
     auto flush_row = [&]() {
         // write the finished row, clear the accumulator, advance to the next row of the block
         const int orow = (a.rowids != nullptr) ? __ldg(a.rowids + row) : row;
-        float* zrow = (orow < a.zsplit) ? a.Z0 + (size_t)orow * a.f
-                                        : a.Z1 + (size_t)(orow - a.zsplit) * a.f;
+        char* zb = (orow < a.zsplit)
+                       ? reinterpret_cast<char*>(a.Z0) + (size_t)(unsigned)orow * pitch
+                       : reinterpret_cast<char*>(a.Z1) + (size_t)(unsigned)(orow - a.zsplit) * pitch;
+        zb += (size_t)f0 * 4;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
             if (fok[v]) {
-                vec_t* zp = reinterpret_cast<vec_t*>(zrow + foff[v]);
+                vec_t* zp = reinterpret_cast<vec_t*>(zb + v * LPE * VW * 4);
                 if (a.beta) vadd(acc[v], *zp);
                 st_out(zp, acc[v]);
             }
@@ -195,66 +212,91 @@ spmm_rowblock_kernel(const SpmmArgs a)
         ++row;
     };
 
-    // software pipeline 1: the (column, value) pair of the NEXT chunk is in flight while the
-    // current chunk's rows are gathered
-    int c_next = 0;
-    float w_next = 0.f;
-    if (e + gl < e_end) {
-        c_next = ld_stream(a.colflag + e + gl);
-        w_next = ld_stream(a.vals + e + gl);
+    auto gather = [&](vec_t (&r)[VPL], int craw) {
+        const unsigned cj = (unsigned)(craw & kColMask);
+        const char* hb = (HALO && cj >= (unsigned)a.split) ? hb1 : hb0;
+        const char* hp = hb + (size_t)cj * pitch;
+#if PGCN_LDMODE >= 2
+        const unsigned long long pol = (craw & kColdFlag) ? pol_cold : pol_hot;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (fok[v]) r[v] = ld_feat_hint(reinterpret_cast<const vec_t*>(hp + v * LPE * VW * 4), pol);
+#else
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (fok[v]) r[v] = ld_feat(reinterpret_cast<const vec_t*>(hp + v * LPE * VW * 4));
+#endif
+    };
+    auto consume = [&](const vec_t (&r)[VPL], int2 cw) {
+        const float w = __int_as_float(cw.y);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (fok[v]) vfma(acc[v], w, r[v]);
+        if (cw.x & lastmask) flush_row();
+    };
+
+    // chunk 0 -> shared; chunk 1 -> registers (in flight)
+    int buf = 0;
+    {
+        int2 cw = make_int2(0, 0);
+        if (e + gl < e_end) { cw.x = ld_stream(a.colflag + e + gl); cw.y = __float_as_int(ld_stream(a.vals + e + gl)); }
+        s_cw[0][threadIdx.x] = cw;
     }
+    int2 cw_next = make_int2(0, 0);
+    if (e + LPE + gl < e_end) {
+        cw_next.x = ld_stream(a.colflag + e + LPE + gl);
+        cw_next.y = __float_as_int(ld_stream(a.vals + e + LPE + gl));
+    }
+    __syncwarp(gmask);
+
     while (e < e_end) {
         const int n = min(LPE, e_end - e);
-        const int c = c_next;
-        const float w = w_next;
-        if (e + LPE + gl < e_end) {
-            c_next = ld_stream(a.colflag + e + LPE + gl);
-            w_next = ld_stream(a.vals + e + LPE + gl);
-        }
-        // software pipeline 2: two register buffers of U gathered rows; the gathers of group g+1 are
-        // issued before group g is consumed. The loop stays rolled (compact SASS: the fully unrolled
-        // first version spent 1/3 of its issue slots waiting on instruction fetch).
-        vec_t rA[U][VPL], rB[U][VPL];
-        int cA[U], cB[U];
-#define PGCN_ISSUE(R, CR, J)                                                                   \
-    _Pragma("unroll") for (int u = 0; u < U; ++u) {                                            \
-        CR[u] = __shfl_sync(gmask, c, (J) + u, LPE);                                           \
-        if ((J) + u < n) {                                                                     \
-            const int cj = CR[u] & kColMask;                                                   \
-            const unsigned long long pol = (CR[u] & kColdFlag) ? pol_cold : pol_hot;           \
-            const float* hrow = (cj < a.split) ? a.H0 + (size_t)cj * a.f                       \
-                                               : a.H1 + (size_t)(cj - a.split) * a.f;         \
-            _Pragma("unroll") for (int v = 0; v < VPL; ++v)                                    \
-                if (fok[v]) R[u][v] = ld_feat_hint(reinterpret_cast<const vec_t*>(hrow + foff[v]), pol); \
-        }                                                                                      \
-    }
-#define PGCN_CONSUME(R, CR, J)                                                                 \
-    _Pragma("unroll") for (int u = 0; u < U; ++u) {                                            \
-        const float wj = __shfl_sync(gmask, w, (J) + u, LPE);                                  \
-        if ((J) + u < n) {                                                                     \
-            _Pragma("unroll") for (int v = 0; v < VPL; ++v)                                    \
-                if (fok[v]) vfma(acc[v], wj, R[u][v]);                                         \
-            if (CR[u] < 0 && !seg) flush_row();                                                \
-        }                                                                                      \
-    }
-        PGCN_ISSUE(rA, cA, 0)
+        const int2* cwp = &s_cw[buf][gbase];
+        vec_t rA[VPL], rB[VPL];
+        int2 cwA = cwp[0], cwB;
+        gather(rA, cwA.x);
+        if (n == LPE) {
+            // full chunk: no bounds predicates inside
 #pragma unroll 1
-        for (int j0 = 0; j0 < n; j0 += 2 * U) {
-            PGCN_ISSUE(rB, cB, j0 + U)
-            PGCN_CONSUME(rA, cA, j0)
-            PGCN_ISSUE(rA, cA, j0 + 2 * U)
-            PGCN_CONSUME(rB, cB, j0 + U)
+            for (int j = 0; j < LPE - 2; j += 2) {
+                cwB = cwp[j + 1];
+                gather(rB, cwB.x);
+                consume(rA, cwA);
+                cwA = cwp[j + 2];
+                gather(rA, cwA.x);
+                consume(rB, cwB);
+            }
+            cwB = cwp[LPE - 1];
+            gather(rB, cwB.x);
+            consume(rA, cwA);
+            consume(rB, cwB);
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < n; j += 2) {
+                const bool hasB = j + 1 < n;
+                if (hasB) { cwB = cwp[j + 1]; gather(rB, cwB.x); }
+                consume(rA, cwA);
+                if (j + 2 < n) { cwA = cwp[j + 2]; gather(rA, cwA.x); }
+                if (hasB) consume(rB, cwB);
+            }
         }
-#undef PGCN_ISSUE
-#undef PGCN_CONSUME
         e += n;
+        // publish the next chunk (it has been in flight since the previous iteration), fetch the one after
+        buf ^= 1;
+        s_cw[buf][threadIdx.x] = cw_next;
+        cw_next = make_int2(0, 0);
+        if (e + LPE + gl < e_end) {
+            cw_next.x = ld_stream(a.colflag + e + LPE + gl);
+            cw_next.y = __float_as_int(ld_stream(a.vals + e + LPE + gl));
+        }
+        __syncwarp(gmask);
     }
 
     if (seg) {
-        float* prow = a.partial + (size_t)(-b.y - 1) * a.f;
+        char* pb = reinterpret_cast<char*>(a.partial) + (size_t)(unsigned)(-b.y - 1) * pitch + (size_t)f0 * 4;
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
-            if (fok[v]) *reinterpret_cast<vec_t*>(prow + foff[v]) = acc[v];
+            if (fok[v]) *reinterpret_cast<vec_t*>(pb + v * LPE * VW * 4) = acc[v];
     }
 }
 

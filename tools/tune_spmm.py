@@ -76,9 +76,8 @@ def main():
             A = sp.coo_matrix((np.ones(n * d, dtype=np.float32), (row, col)), shape=(n, n))
             p = planmod.build_plan(A, np.zeros(n, dtype=np.int64), 0, 1, f, device=dev)
             H = torch.rand((n, f), device=dev); Z = torch.empty((n, f), device=dev)
-            for tile, unroll in ((0, 2), (0, 4), (0, 8), (32, 4)):
+            for tile, unroll in ((0, 0), (32, 0)):
                 p.set_option("tile_floats", tile)
-                p.set_option("unroll", unroll)
                 med, mn = timed(lambda: cabi.check(lib.pgcn_spmm(p.handle, 0, H.data_ptr(), None, Z.data_ptr(), None, f, stream), p.handle), args.iters)
                 nnz = p.lp.nnz()
                 emit({"probe": "gather", "window_rows": W, "window_MB": W * f * 4 / 1e6, "tile_floats": tile, "unroll": unroll, "ms": med,
@@ -118,14 +117,17 @@ def main():
         opts = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.single.split(",") if kv}
         point(opts)
     elif args.sweep == "default":
-        for epb, tile, unroll in itertools.product((64, 128, 256, 512), (0, 64, 32, 16), (2, 4, 8)):
-            point({"edges_per_block": epb, "tile_floats": tile, "unroll": unroll})
+        for epb, tile in itertools.product((64, 128, 256, 512), (0, 64, 32, 16)):
+            point({"edges_per_block": epb, "tile_floats": tile})
+    elif args.sweep == "epb":
+        for epb, lr in itertools.product((64, 96, 128, 160, 192, 256, 384), (0, 100000)):
+            point({"edges_per_block": epb, "tile_floats": 0, "long_row": lr})
     elif args.sweep == "mini":
-        for epb, unroll in itertools.product((128, 160), (2, 4)):
-            point({"edges_per_block": epb, "tile_floats": 0, "unroll": unroll})
+        for epb in (128, 160):
+            point({"edges_per_block": epb, "tile_floats": 0})
     elif args.sweep == "small":
-        for epb, unroll in itertools.product((96, 128, 192, 256), (2, 4, 8)):
-            point({"edges_per_block": epb, "tile_floats": 0, "unroll": unroll})
+        for epb in (96, 128, 192, 256):
+            point({"edges_per_block": epb, "tile_floats": 0})
     elif args.sweep == "fine":
         for epb, tile, lr in itertools.product((96, 128, 192, 256, 384), (0, 64, 32), (0, 256, 1024, 4096)):
             point({"edges_per_block": epb, "tile_floats": tile, "long_row": lr})
