@@ -222,6 +222,7 @@ def main():
     nnz_total = int(A.nnz)
     del A
     plan = planmod.PgcnPlan(lp, f, device=device)
+    tuned = plan.autotune(f)          # set-up, untimed: like the reference's plan building
     for kv in args.opt:
         name, v = kv.split("=")
         plan.set_option(name, int(v))

@@ -107,6 +107,13 @@ int pgcn_plan_destroy(pgcn_plan* plan);
 int pgcn_plan_set_option(pgcn_plan* plan, const char* name, int64_t value);
 int64_t pgcn_plan_get_option(const pgcn_plan* plan, const char* name);
 
+/*
+ * Time the forward SpMM of this plan at feature width f for a few "edges_per_block" values on
+ * scratch buffers and keep the fastest (set-up work, like the reference's untimed plan building,
+ * GPU/PGCN.py:171-200). Synchronous. Returns the chosen value (>0) or a negative pgcn_status.
+ */
+int pgcn_plan_autotune(pgcn_plan* plan, int32_t f);
+
 /* Plan-owned device slabs (f_max floats per row), for callers that want zero-copy access:
  * which = 0 send slab (S rows), 1 halo/recv slab (h rows), 2 reverse recv slab (S rows),
  * 3 reverse send slab (h rows: halo partials of A^T g). */

@@ -648,6 +648,50 @@ int64_t pgcn_plan_get_option(const pgcn_plan* p, const char* name)
     return PGCN_ERR_INVALID;
 }
 
+int pgcn_plan_autotune(pgcn_plan* p, int32_t f)
+{
+    int rc = check_f(p, f);
+    if (rc) return rc;
+    if (p->fwd.nnz == 0) return (int)p->opt_epb;
+    CU(p, cudaSetDevice(p->device));
+    float *H0 = nullptr, *H1 = nullptr, *Z = nullptr;
+    const size_t bm = std::max<size_t>((size_t)p->m * f, 1) * 4, bh = std::max<size_t>((size_t)p->h * f, 1) * 4;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(H0); cudaFree(H1); cudaFree(Z);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    };
+    if (cudaMalloc((void**)&H0, bm) != cudaSuccess || cudaMalloc((void**)&H1, bh) != cudaSuccess ||
+        cudaMalloc((void**)&Z, bm) != cudaSuccess) {
+        cleanup(); cudaGetLastError();
+        return fail(p, PGCN_ERR_CUDA, "autotune: scratch allocation failed");
+    }
+    cudaMemsetAsync(H0, 0, bm, p->host_stream); cudaMemsetAsync(H1, 0, bh, p->host_stream);
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    static const int cand[] = {96, 112, 128, 144, 160, 192, 256};
+    const int64_t keep_epb = p->opt_epb;
+    int best = (int)keep_epb;
+    float best_ms = 1e30f;
+    for (int c : cand) {
+        p->opt_epb = c;
+        float ms_min = 1e30f;
+        for (int it = 0; it < 4; ++it) {                 // first pass also builds the schedule
+            cudaEventRecord(e0, p->host_stream);
+            rc = launch_spmm(p, p->fwd, H0, p->h ? H1 : nullptr, p->m, Z, nullptr, p->m, f, 0, p->host_stream);
+            cudaEventRecord(e1, p->host_stream);
+            if (rc || cudaEventSynchronize(e1) != cudaSuccess) { cleanup(); p->opt_epb = keep_epb; return rc ? rc : fail(p, PGCN_ERR_CUDA, "autotune: kernel failed"); }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (it > 0) ms_min = std::min(ms_min, ms);
+        }
+        if (ms_min < best_ms) { best_ms = ms_min; best = c; }
+    }
+    p->opt_epb = best;
+    cleanup();
+    return best;
+}
+
 void* pgcn_plan_slab(pgcn_plan* p, int which)
 {
     if (!p) return nullptr;

@@ -39,7 +39,7 @@ constexpr int kColdFlag = 0x40000000;
 constexpr int kColMask = 0x3fffffff;
 
 #ifndef PGCN_LDMODE
-#define PGCN_LDMODE 0      // 0: ld.global.nc   1: + L1::no_allocate   2: L2 hot/cold hints   3: 2 + L1::no_allocate
+#define PGCN_LDMODE 2      // 0: ld.global.nc   1: + L1::no_allocate   2: L2 hot/cold hints   3: 2 + L1::no_allocate
 #endif
 
 struct SpmmArgs {
@@ -252,6 +252,8 @@ spmm_rowblock_kernel(const SpmmArgs a)
     while (e < e_end) {
         const int n = min(LPE, e_end - e);
         const int2* cwp = &s_cw[buf][gbase];
+        // two register buffers: edge j+1 is gathered before edge j is consumed. (A ring of 4 buffers
+        // was measured 27 % SLOWER on C2: 1.31 vs 1.03 ms — deeper per-warp pipelines lose to occupancy.)
         vec_t rA[VPL], rB[VPL];
         int2 cwA = cwp[0], cwB;
         gather(rA, cwA.x);

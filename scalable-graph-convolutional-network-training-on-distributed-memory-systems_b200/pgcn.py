@@ -98,6 +98,7 @@ def run(rank, size, nlayers, nfeatures, path_A, path_partvec, backend, ref_quirk
     if ref_quirks:
         transport = "nccl"            # the quirk emulation drives the exchange step by step (NCCL entry points)
     used = plan.init_comm(transport=transport)
+    plan.autotune(nfeatures)
     lp = plan.lp
 
     own = torch.from_numpy(lp.owned).to(device)

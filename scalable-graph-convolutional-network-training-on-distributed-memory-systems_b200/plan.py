@@ -224,6 +224,12 @@ class PgcnPlan:
     def get_option(self, name):
         return int(self._lib.pgcn_plan_get_option(self.handle, name.encode()))
 
+    def autotune(self, f):
+        """Pick the fastest edges_per_block for this matrix at width f (set-up work). Returns it."""
+        import torch
+        with torch.cuda.device(self.device):
+            return cabi.check(self._lib.pgcn_plan_autotune(self.handle, int(f)), self._h)
+
     def algorithmic_bytes(self, f):
         b = cabi.PgcnBytes()
         cabi.check(self._lib.pgcn_algorithmic_bytes(self.handle, int(f), C.byref(b)), self._h)

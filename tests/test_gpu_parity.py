@@ -249,6 +249,20 @@ def test_full_size_properties_config_C2():
     p.close()
 
 
+def test_autotune_keeps_results():
+    n, f = 6000, 128
+    A = skewed_graph(n, 150000, seed=13)
+    H = np.random.RandomState(4).uniform(-1, 1, size=(n, f)).astype(np.float32)
+    p = make_plans(A, np.zeros(n, dtype=np.int64), 1, f)[0]
+    z0 = forward_all([p], H)[0]
+    chosen = p.autotune(f)
+    assert chosen in (96, 112, 128, 144, 160, 192, 256) and p.get_option("edges_per_block") == chosen
+    z1 = forward_all([p], H)[0]
+    assert_close_fp32(z1.cpu().numpy(), orc.truth_forward(A, H), fp32_tol(A, H, int(orc.row_degree(A).max())), "autotuned")
+    torch.testing.assert_close(z0, z1, rtol=1e-4, atol=1e-5)
+    p.close()
+
+
 def test_forward_host_entry_point():
     """pgcn_forward_host: the call a C host binds (host buffers in, host buffers out)."""
     import ctypes as C

@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--transpose", action="store_true")
     ap.add_argument("--cache", default="/tmp/pgcn_b200_cache")
     ap.add_argument("--out", default="")
+    ap.add_argument("--hot-sweep", default="", help="comma list of hot-set sizes in MB (rebuilds the plan each time)")
     args = ap.parse_args()
 
     import torch
@@ -101,24 +102,37 @@ def main():
     alg = ab["spmm_bwd"] if args.transpose else ab["spmm_fwd"]
 
     def run():
+        nonlocal p
         if args.transpose:
             cabi.check(lib.pgcn_spmm(p.handle, 1, H.data_ptr(), None, Z.data_ptr(), None, f, stream), p.handle)
         else:
             cabi.check(lib.pgcn_spmm(p.handle, 0, H.data_ptr(), None, Z.data_ptr(), None, f, stream), p.handle)
 
     def point(opts):
+        nonlocal p
         for k_, v in opts.items():
             p.set_option(k_, v)
         med, mn = timed(run, args.iters)
         emit(dict(opts, ms=med, ms_min=mn, edges_per_s=lp.nnz() / med * 1e3, alg_GBs=alg / med / 1e6,
                   frac=alg / med / 1e6 / peak, gather_GBs=ab["gather_fwd"] / med / 1e6))
 
-    if args.single:
+    if args.hot_sweep:
+        for hot in [int(x) for x in args.hot_sweep.split(",")]:
+            os.environ["PGCN_HOT_MB"] = str(hot)
+            p.close()
+            p = planmod.PgcnPlan(lp, f, device=dev)
+            for epb in (128, 192):
+                point({"edges_per_block": epb, "hot_mb_env": hot} if False else {"edges_per_block": epb})
+                print(json.dumps({"hot_mb": hot}), flush=True)
+    elif args.single:
         opts = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.single.split(",") if kv}
         point(opts)
     elif args.sweep == "default":
         for epb, tile in itertools.product((64, 128, 256, 512), (0, 64, 32, 16)):
             point({"edges_per_block": epb, "tile_floats": tile})
+    elif args.sweep == "depth":
+        for epb in (96, 112, 120, 128, 136, 144, 152, 160, 192):
+            point({"edges_per_block": epb})
     elif args.sweep == "epb":
         for epb, lr in itertools.product((64, 96, 128, 160, 192, 256, 384), (0, 100000)):
             point({"edges_per_block": epb, "tile_floats": 0, "long_row": lr})
