@@ -150,6 +150,9 @@ int pgcn_p2p_import(pgcn_plan* plan, const void* handles_k);
  *   transpose = 1 : A^T (m+h rows). H_own is the m x f upstream gradient, H_halo ignored.
  *                   Rows [0,m) go to Z (m x f), rows [m, m+h) go to Z_halo (h x f), already in
  *                   the wire order of the reverse exchange.
+ *   transpose = 2 : own-columns half of the overlapped forward, Z  = A_own  * H_own
+ *   transpose = 3 : halo-columns half,                          Z += A_halo * H_halo
+ *                   (Parallel-GCN/main.c:271 then :295; plans with k > 1 and h > 0 only)
  */
 int pgcn_spmm(pgcn_plan* plan, int transpose,
               const float* H_own, const float* H_halo,

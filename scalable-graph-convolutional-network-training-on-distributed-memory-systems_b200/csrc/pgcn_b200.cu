@@ -185,22 +185,18 @@ int upload(pgcn_plan* p, T** dst, const T* src, size_t n)
 // Upload one CSR. Rows without entries are squeezed out of the walked row space (their outputs are
 // zero-filled by a separate launch); `ext_rowmap` maps the rows of an already-compact matrix (the
 // halo-column part, which only holds boundary rows) to output rows.
-// `col_refs[j]` = number of stored entries in column j (null: no hot/cold marking): columns are
-// ranked by it and only as many of the most-referenced rows of H as fit `hot_rows` stay unmarked;
-// every other column gets kColdFlag and is gathered with an L2 evict_first policy.
+// `col_refs[j]` = number of stored entries in column j and `cold_thresh` the reference count at or
+// below which a column is COLD (-1: no marking): cold columns get kColdFlag and are gathered with an
+// L2 evict_first policy, the most-referenced rows of H (as many as fit the hot budget) evict_last.
 int csr_upload(pgcn_plan* p, DevCsr& c, int nrows, const int* rowptr, const int* colidx, const float* vals,
-               const std::vector<int>* ext_rowmap = nullptr, const int* col_refs = nullptr, int ncols = 0,
-               int64_t hot_rows = 0)
+               const std::vector<int>* ext_rowmap = nullptr, const int* col_refs = nullptr, int cold_thresh = -1)
 {
     c.nrows = nrows;
     c.nnz = rowptr[nrows];
     std::vector<int> colflag(colidx, colidx + c.nnz);
-    if (col_refs && ncols > hot_rows && hot_rows > 0) {
-        std::vector<int> sorted(col_refs, col_refs + ncols);
-        std::nth_element(sorted.begin(), sorted.begin() + (ncols - hot_rows), sorted.end());
-        const int thresh = sorted[ncols - hot_rows];          // columns with refs <= thresh are cold
+    if (col_refs && cold_thresh >= 0) {
         for (int64_t e = 0; e < c.nnz; ++e)
-            if (col_refs[colidx[e]] <= thresh) colflag[e] |= kColdFlag;
+            if (col_refs[colidx[e]] <= cold_thresh) colflag[e] |= kColdFlag;
     }
     std::vector<int> rowids, empty;
     c.h_rowptr.clear();
@@ -529,8 +525,16 @@ int pgcn_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* 
     // rows of H kept hot in L2: about half of the 126 MB L2, the rest is left to the streams
     if (const char* e = getenv("PGCN_HOT_MB")) p->opt_hot_mb = std::max<long long>(0, atoll(e));   // tuning knob
     const int64_t hot_rows = std::max<int64_t>(1, (p->opt_hot_mb << 20) / ((int64_t)f_max * 4));
-    TRY(csr_upload(p, p->fwd, m, rowptr, colidx, vals, nullptr, refs_fwd.data(), m + h, hot_rows));
-    TRY(csr_upload(p, p->tr, m + h, t_rowptr, t_colidx, t_vals, nullptr, refs_tr.data(), m, hot_rows));
+    auto cold_threshold = [&](const std::vector<int>& refs) -> int {
+        const int64_t ncols = (int64_t)refs.size();
+        if (ncols <= hot_rows) return -1;                  // everything fits: nothing is cold
+        std::vector<int> sorted(refs);
+        std::nth_element(sorted.begin(), sorted.begin() + (ncols - hot_rows), sorted.end());
+        return sorted[ncols - hot_rows];
+    };
+    const int cold_fwd = cold_threshold(refs_fwd), cold_tr = cold_threshold(refs_tr);
+    TRY(csr_upload(p, p->fwd, m, rowptr, colidx, vals, nullptr, refs_fwd.data(), cold_fwd));
+    TRY(csr_upload(p, p->tr, m + h, t_rowptr, t_colidx, t_vals, nullptr, refs_tr.data(), cold_tr));
 
     // distinct referenced columns / transposed rows (for the roofline's compulsory bytes)
     for (int r = 0; r < m + h; ++r) if (t_rowptr[r + 1] > t_rowptr[r]) ++p->cols_ref;
@@ -546,13 +550,13 @@ int pgcn_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* 
             const size_t before = h_ci.size();
             for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
                 if (colidx[e] < m) { o_ci.push_back(colidx[e]); o_v.push_back(vals[e]); }
-                else { h_ci.push_back(colidx[e]); h_v.push_back(vals[e]); }
+                else { h_ci.push_back(colidx[e] - m); h_v.push_back(vals[e]); }   // slab-relative column
             }
             o_rp[r + 1] = (int)o_ci.size();
             if (h_ci.size() > before) { h_map.push_back(r); h_rp.push_back((int)h_ci.size()); }
         }
-        TRY(csr_upload(p, p->own, m, o_rp.data(), o_ci.data(), o_v.data(), nullptr, refs_fwd.data(), m + h, hot_rows));
-        TRY(csr_upload(p, p->halo, (int)h_map.size(), h_rp.data(), h_ci.data(), h_v.data(), &h_map, refs_fwd.data(), m + h, hot_rows));
+        TRY(csr_upload(p, p->own, m, o_rp.data(), o_ci.data(), o_v.data(), nullptr, refs_fwd.data(), cold_fwd));
+        TRY(csr_upload(p, p->halo, (int)h_map.size(), h_rp.data(), h_ci.data(), h_v.data(), &h_map, refs_fwd.data() + m, cold_fwd));
         p->have_split = true;
     }
 
@@ -800,10 +804,21 @@ int pgcn_spmm(pgcn_plan* p, int transpose, const float* H_own, const float* H_ha
     int rc = check_f(p, f);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (transpose == 2 || transpose == 3) {
+        // the two halves of the overlapped forward, individually callable (k > 1 plans only)
+        if (!p->have_split) return fail(p, PGCN_ERR_STATE, "plan has no own/halo split (k == 1 or h == 0)");
+        if (!Z) return fail(p, PGCN_ERR_INVALID, "null Z");
+        if (transpose == 2) {
+            if (!H_own) return fail(p, PGCN_ERR_INVALID, "null H_own");
+            return launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, f, 0, st);
+        }
+        if (!H_halo) return fail(p, PGCN_ERR_INVALID, "null H_halo");
+        return launch_spmm(p, p->halo, H_halo, nullptr, p->h, Z, nullptr, p->m, f, 1, st);
+    }
     if (!transpose) {
         if (p->m > 0 && (!H_own || !Z)) return fail(p, PGCN_ERR_INVALID, "null H_own/Z");
         if (p->h > 0 && !H_halo) return fail(p, PGCN_ERR_INVALID, "h=%d but H_halo is null", p->h);
-        return launch_spmm(p, p->fwd, H_own, H_halo, p->m, Z, nullptr, p->m, f, 0, st);
+        return launch_spmm(p, p->fwd, H_own, p->h > 0 ? H_halo : nullptr, p->m, Z, nullptr, p->m, f, 0, st);
     }
     if (p->m > 0 && (!H_own || !Z)) return fail(p, PGCN_ERR_INVALID, "null gZ/G");
     if (p->h > 0 && !Z_halo) return fail(p, PGCN_ERR_INVALID, "h=%d but Z_halo is null", p->h);
@@ -840,7 +855,7 @@ int pgcn_forward(pgcn_plan* p, const float* H_own, float* Z, int32_t f, void* st
     if (p->m > 0 && (!H_own || !Z)) return fail(p, PGCN_ERR_INVALID, "null H_own/Z");
     cudaStream_t st = (cudaStream_t)stream;
     if (p->k == 1)
-        return launch_spmm(p, p->fwd, H_own, p->d_halo_slab, p->m, Z, nullptr, p->m, f, 0, st);
+        return launch_spmm(p, p->fwd, H_own, p->h > 0 ? p->d_halo_slab : nullptr, p->m, Z, nullptr, p->m, f, 0, st);
 
     const bool split = p->have_split && p->opt_overlap;
     if (p->p2p && (f % 4 == 0)) {
@@ -862,7 +877,7 @@ int pgcn_forward(pgcn_plan* p, const float* H_own, float* Z, int32_t f, void* st
             if ((rc = launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, f, 0, st))) return rc;
             if ((rc = p2p_signal_wait(p, st, false, true))) return rc;
             CU(p, cudaStreamWaitEvent(st, p->ev_b, 0));          // H_own is free for the caller after this
-            return launch_spmm(p, p->halo, H_own, halo, p->m, Z, nullptr, p->m, f, 1, st);
+            return launch_spmm(p, p->halo, halo, nullptr, p->h, Z, nullptr, p->m, f, 1, st);
         }
         if ((rc = launch_pack(p, H_own, nullptr, dst, f, st))) return rc;
         if ((rc = p2p_signal_wait(p, st, true, true))) return rc;
@@ -878,7 +893,7 @@ int pgcn_forward(pgcn_plan* p, const float* H_own, float* Z, int32_t f, void* st
         CU(p, cudaEventRecord(p->ev_b, p->comm_stream));
         if ((rc = launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, f, 0, st))) return rc;
         CU(p, cudaStreamWaitEvent(st, p->ev_b, 0));
-        return launch_spmm(p, p->halo, H_own, p->d_halo_slab, p->m, Z, nullptr, p->m, f, 1, st);
+        return launch_spmm(p, p->halo, p->d_halo_slab, nullptr, p->h, Z, nullptr, p->m, f, 1, st);
     }
     if ((rc = launch_pack(p, H_own, p->d_send_slab, nullptr, f, st))) return rc;
     if ((rc = nccl_exchange(p, p->d_send_slab, p->d_halo_slab, f, 0, st))) return rc;

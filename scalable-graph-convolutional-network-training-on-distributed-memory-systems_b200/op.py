@@ -113,6 +113,21 @@ def spmm_local(plan, H_own, H_halo=None, transpose=False):
         return G, Gh
 
 
+def spmm_split(plan, H_own, H_halo):
+    """The overlapped forward's two kernels back to back: Z = A_own*H_own, then Z += A_halo*H_halo
+    (Parallel-GCN/main.c:271,295). Same result as spmm_local up to fp32 summation order."""
+    lp = plan.lp
+    H_own = _check_feat(plan, H_own, lp.m, "H_own")
+    H_halo = _check_feat(plan, H_halo, lp.h, "H_halo")
+    f = H_own.shape[1]
+    Z = torch.empty((lp.m, f), dtype=torch.float32, device=H_own.device)
+    lib = cabi.load()
+    with torch.cuda.device(H_own.device):
+        cabi.check(lib.pgcn_spmm(plan.handle, 2, H_own.data_ptr(), None, Z.data_ptr(), None, f, _stream_ptr()), plan.handle)
+        cabi.check(lib.pgcn_spmm(plan.handle, 3, None, H_halo.data_ptr(), Z.data_ptr(), None, f, _stream_ptr()), plan.handle)
+    return Z
+
+
 def pack_rows(plan, H_own):
     """send slab [S, f]: H[send_map[p]] for every peer p, concatenated in peer order (GPU/PGCN.py:104)."""
     H_own = _check_feat(plan, H_own, plan.lp.m, "H_own")

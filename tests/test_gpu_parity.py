@@ -249,6 +249,27 @@ def test_full_size_properties_config_C2():
     p.close()
 
 
+@pytest.mark.parametrize("case", ["gemat11_k2", "gemat11_k3_hp", "gemat11_k3_rp", "karate_k3_hp"])
+def test_overlap_halves_equal_single_pass(case):
+    """The own-columns / halo-columns kernels of the overlapped forward (what runs on > 1 GPU) on one GPU."""
+    from pgcn_b200 import op
+    g = Golden(case)
+    plans = make_plans(g.A, g.partvec, g.k, g.f)
+    Z = forward_all(plans, g.H)
+    Z64 = orc.truth_forward(g.A, g.H)
+    tol = fp32_tol(g.A, g.H, int(orc.row_degree(g.A).max()))
+    for r, p in enumerate(plans):
+        lp = p.lp
+        if lp.h == 0:
+            continue
+        zs = op.spmm_split(p, t(g.H[lp.owned]), t(g.H[lp.halo]))
+        assert_close_fp32(zs.cpu().numpy(), Z64[lp.owned], tol[lp.owned], "%s split r%d" % (case, r))
+        np.testing.assert_allclose(zs.cpu().numpy(), g.get(r, "Z1_own"), rtol=2e-5, atol=2e-6 * max(1.0, np.abs(Z64).max()))
+        torch.testing.assert_close(zs, Z[r], rtol=1e-4, atol=1e-5)
+    for p in plans:
+        p.close()
+
+
 def test_autotune_keeps_results():
     n, f = 6000, 128
     A = skewed_graph(n, 150000, seed=13)

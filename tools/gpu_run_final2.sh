@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "overlap or golden or autotune or tiny or widths" ) > gpurun_out/pytest_gpu_final2.log 2>&1
+tail -2 gpurun_out/pytest_gpu_final2.log
+timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_n1_final.json 2> gpurun_out/bench_n1_final.err
+cut -c1-1500 gpurun_out/bench_n1_final.json
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:spmm_rowblock -s 3 -c 2 -f -o gpurun_out/prof_c2_final \
+    python tools/tune_spmm.py --config C2 --single edges_per_block=144 --iters 3 > gpurun_out/ncu_final.log 2>&1
+tail -2 gpurun_out/ncu_final.log | cut -c1-200
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_final.csv \
+    python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_final.log 2>&1
+grep -c spmm_rowblock gpurun_out/launches_final.csv
