@@ -367,10 +367,10 @@ int launch_spmm(pgcn_plan* p, DevCsr& c, const float* H0, const float* H1, int s
         FixupArgs fa;
         fa.long_rows = c.d_long; fa.nlong = c.nlong; fa.partial = c.d_partial;
         fa.Z0 = Z0; fa.Z1 = Z1; fa.zsplit = zsplit; fa.rowids = c.d_rowids; fa.f = f; fa.beta = beta;
-        const long long total = (long long)c.nlong * (f / t.vw);
-        const unsigned grid = (unsigned)((total + 255) / 256);
-        if (t.vw == 4) spmm_fixup_kernel<4><<<grid, 256, 0, st>>>(fa);
-        else spmm_fixup_kernel<1><<<grid, 256, 0, st>>>(fa);
+        const int nvec = f / t.vw;
+        const unsigned grid = (unsigned)c.nlong * (unsigned)((nvec + 31) / 32);
+        if (t.vw == 4) spmm_fixup_kernel<4><<<grid, 32 * kFixupGroups, 0, st>>>(fa);
+        else spmm_fixup_kernel<1><<<grid, 32 * kFixupGroups, 0, st>>>(fa);
         ++p->launches;
     }
     CU(p, cudaGetLastError());
