@@ -192,6 +192,12 @@ def run_reference(args):
 
 def main():
     args = parse()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # started plainly: re-launch one rank per GPU (the driver launches torch.distributed.run itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
     if args.impl == "reference":
         return run_reference(args)
 

@@ -90,11 +90,16 @@ def run(rank, size, nlayers, nfeatures, path_A, path_partvec, backend, ref_quirk
                            "(no CPU fallback); use -b nccl" % backend)
     device = torch.device("cuda", rank % torch.cuda.device_count())      # GPU/PGCN.py:169
     torch.cuda.set_device(device)
-    A = graphio.read_adjacency(path_A)                                   # :171
-    n = A.shape[0]
-    partvec = graphio.read_partvec(path_partvec, n)                      # :172-173
-    graphio.check_partvec(partvec, size)
-    plan = planmod.build_plan(A, partvec, rank, size, nfeatures, device=device)   # :175-182
+    cache = os.environ.get("PGCN_PLAN_CACHE")
+    if cache:                                                            # optional on-disk plan cache (§8f rank 2)
+        lp_host = planmod.cached_local_plan(path_A, path_partvec, rank, size, cache)
+    else:
+        A = graphio.read_adjacency(path_A)                               # :171
+        partvec = graphio.read_partvec(path_partvec, A.shape[0])         # :172-173
+        graphio.check_partvec(partvec, size)
+        lp_host = planmod.build_local_plan(A, partvec, rank, size)       # :175-176
+    n = lp_host.n
+    plan = planmod.PgcnPlan(lp_host, nfeatures, device=device)           # :178-182
     if ref_quirks:
         transport = "nccl"            # the quirk emulation drives the exchange step by step (NCCL entry points)
     used = plan.init_comm(transport=transport)

@@ -153,6 +153,47 @@ def build_local_plan(A, partvec, rank, size):
     return lp
 
 
+_LP_ARRAYS = ("owned", "halo", "rowptr", "colidx", "vals", "t_rowptr", "t_colidx", "t_vals",
+              "send_idx", "send_gid", "send_off", "recv_off")
+
+
+def save_local_plan(path, lp):
+    """Binary cache of one rank's plan: the reference re-reads the .mtx and re-walks
+    every nnz on every rank at every start (GPU/PGCN.py:171-176)."""
+    np.savez(path, meta=np.array([lp.n, lp.k, lp.rank, lp.m, lp.h, lp.S], dtype=np.int64),
+             **{name: getattr(lp, name) for name in _LP_ARRAYS})
+
+
+def load_local_plan(path):
+    z = np.load(path)
+    lp = LocalPlan()
+    lp.n, lp.k, lp.rank, lp.m, lp.h, lp.S = [int(x) for x in z["meta"]]
+    for name in _LP_ARRAYS:
+        setattr(lp, name, z[name])
+    return lp
+
+
+def cached_local_plan(path_A, path_partvec, rank, size, cache_dir):
+    """build_local_plan with an on-disk cache keyed by the two input files (size + mtime), rank and size."""
+    import hashlib
+    import os
+    from . import graphio
+    key = hashlib.sha1(repr([os.path.abspath(path_A), os.path.getsize(path_A), int(os.path.getmtime(path_A)),
+                             os.path.abspath(path_partvec), os.path.getsize(path_partvec),
+                             int(os.path.getmtime(path_partvec)), rank, size]).encode()).hexdigest()[:16]
+    os.makedirs(cache_dir, exist_ok=True)
+    path = os.path.join(cache_dir, "plan_%s_r%dof%d.npz" % (key, rank, size))
+    if os.path.exists(path):
+        return load_local_plan(path)
+    A = graphio.read_adjacency(path_A)
+    pv = graphio.check_partvec(graphio.read_partvec(path_partvec, A.shape[0]), size)
+    lp = build_local_plan(A, pv, rank, size)
+    tmp = path + ".%d.tmp.npz" % os.getpid()
+    save_local_plan(tmp, lp)
+    os.replace(tmp, path)
+    return lp
+
+
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 
@@ -250,6 +291,7 @@ class PgcnPlan:
             raise RuntimeError("torch.distributed must be initialised before PgcnPlan.init_comm")
         # collectives of the set-up phase run on whatever backend the process group has
         cdev = self.device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        used = None
         if transport in ("p2p", "auto"):
             blob = C.create_string_buffer(cabi.P2P_HANDLE_BYTES)
             with torch.cuda.device(self.device):
@@ -267,9 +309,12 @@ class PgcnPlan:
                 dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
                 if int(ok.item()) == 1:
                     dist.barrier(group=group)
-                    return "p2p"
-            if transport == "p2p":
+                    used = "p2p"
+            if used is None and transport == "p2p":
                 cabi.check(rc if rc < 0 else -5, self._h)
+        # the NCCL communicator is always created: it is the transport of the step-by-step entry points
+        # (pgcn_exchange) and the fallback of the fused ones for widths the peer-store kernels do not take
+        # (f % 4 != 0)
         ident = torch.zeros(cabi.NCCL_ID_BYTES, dtype=torch.uint8)
         if self.lp.rank == 0:
             buf = C.create_string_buffer(cabi.NCCL_ID_BYTES)
@@ -280,7 +325,7 @@ class PgcnPlan:
         raw = bytes(ident.cpu().numpy().tobytes())
         with torch.cuda.device(self.device):
             cabi.check(self._lib.pgcn_comm_init(self.handle, raw), self._h)
-        return "nccl"
+        return used or "nccl"
 
     # -- stats, as the reference counts them (rows, messages incl. empty ones) -------------------
     def count_exchange(self, backward=False):

@@ -64,6 +64,16 @@ def _worker(rank, k, port, case, transport, q):
             np.testing.assert_allclose(res[1][0], gold.get(rank, "Z1_own"), rtol=2e-5, atol=2e-6 * max(1.0, np.abs(Z64).max()))
             if k <= 2:     # Q3 cannot bite with two ranks: the reference gradient is right
                 np.testing.assert_allclose(res[1][1], gold.get(rank, "Hgrad_own"), rtol=2e-5, atol=2e-6 * max(1.0, np.abs(G64).max()))
+        # a width the peer-store kernels do not take (f % 4 != 0) goes through the NCCL fallback
+        st0 = dict(p.stats)
+        Hodd = torch.from_numpy(np.ascontiguousarray(H[own][:, :6])).cuda().requires_grad_(True)
+        Zodd = PSpMM.apply(p, Hodd)
+        Zodd.backward(torch.from_numpy(np.ascontiguousarray(G[own][:, :6])).cuda())
+        torch.cuda.synchronize()
+        Z64o = orc.truth_forward(A, H[:, :6])[own]; G64o = orc.truth_backward(A, G[:, :6])[own]
+        assert (np.abs(Zodd.detach().cpu().numpy() - Z64o) <= fp32_tol(A, H[:, :6], int(orc.row_degree(A).max()))[own]).all()
+        assert (np.abs(Hodd.grad.cpu().numpy() - G64o) <= fp32_tol(A.T, G[:, :6], int(orc.row_degree(A.T).max()))[own]).all()
+        p.stats.update(st0)
         # stats as the reference counts them: rows, messages incl. empty ones; 2 fwd+bwd pairs + 5 fwd
         st = p.stats
         assert st["send_nmsg"] == (2 * 2 + 5) * (k - 1)

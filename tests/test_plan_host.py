@@ -112,3 +112,20 @@ def test_mtx_loader_matches_scipy(tmp_path):
     graphio.save_adjacency_npz(str(tmp_path / "a.npz"), A)
     Cc = graphio.read_adjacency(str(tmp_path / "a.npz"))
     assert abs(sp.csr_matrix(Cc) - sp.csr_matrix(A)).max() < 1e-7
+
+
+def test_plan_cache_roundtrip(tmp_path):
+    from scipy.io import mmwrite
+    g = Golden("gemat11_k3_hp")
+    a = str(tmp_path / "g.mtx"); mmwrite(a, g.A, precision=17)
+    pv = str(tmp_path / "g.mtx.3.hp"); graphio.write_partvec(pv, g.partvec)
+    cache = str(tmp_path / "cache")
+    lp1 = planmod.cached_local_plan(a, pv, 1, 3, cache)          # builds and stores
+    lp2 = planmod.cached_local_plan(a, pv, 1, 3, cache)          # loads
+    ref = planmod.build_local_plan(g.A, g.partvec, 1, 3)
+    for name in planmod._LP_ARRAYS:
+        assert np.array_equal(getattr(lp1, name), getattr(ref, name)), name
+        assert np.array_equal(getattr(lp2, name), getattr(ref, name)), name
+        assert getattr(lp2, name).dtype == getattr(ref, name).dtype, name
+    assert (lp2.n, lp2.k, lp2.rank, lp2.m, lp2.h, lp2.S) == (ref.n, ref.k, ref.rank, ref.m, ref.h, ref.S)
+    assert len([f for f in __import__("os").listdir(cache) if f.endswith(".npz")]) == 1
