@@ -57,6 +57,94 @@ def check_partvec(partvec, size):
 
 
 # ------------------------------------------------------------------------------------------
+# on-disk formats of the CPU path (GCN-HP/main.cpp writers -> Parallel-GCN/main.c readers)
+# ------------------------------------------------------------------------------------------
+
+def read_cpu_config(path):
+    """`config`: "nlayers n f ... f fout" (GCN-HP/main.cpp:117-131, parsed by Parallel-GCN/main.c:687-698)."""
+    vals = [int(x) for x in open(path).read().split()]
+    return {"nlayers": vals[0], "n": vals[1], "widths": vals[2:]}
+
+
+def read_cpu_matrix_part(path):
+    """`A.k` / `Y.k`: header "n nnz_k", then "i j val" with 0-based GLOBAL indices, values printed %.2f
+    (GCN-HP/main.cpp:213-249; read by Parallel-GCN/main.c:609-647). Returns (n, row, col, val)."""
+    with open(path) as f:
+        n, nnz = [int(x) for x in f.readline().split()]
+        data = np.loadtxt(f, dtype=np.float64, ndmin=2) if nnz else np.zeros((0, 3))
+    if data.shape[0] != nnz:
+        raise ValueError("%s: header says %d entries, file has %d" % (path, nnz, data.shape[0]))
+    return n, data[:, 0].astype(np.int64), data[:, 1].astype(np.int64), data[:, 2].astype(np.float32)
+
+
+def read_cpu_rows_part(path):
+    """`H.k`: the number of rows of part k, then one owned global row id per line
+    (GCN-HP/main.cpp:251-282; Parallel-GCN/main.c:650-684 sets H0 = 1.0 on exactly these rows)."""
+    vals = np.array(open(path).read().split(), dtype=np.int64)
+    if vals.size == 0 or vals[0] != vals.size - 1:
+        raise ValueError("%s: row count does not match" % path)
+    return vals[1:]
+
+
+def read_cpu_conn(path):
+    """`conn.k`: "nsend nrecv", then one line per target: "target count id id ..." — the vertices part k
+    sends to each target (GCN-HP/main.cpp:147-185; Parallel-GCN/main.c:526-551). Returns {target: ids}."""
+    lines = open(path).read().splitlines()
+    nsend, _ = [int(x) for x in lines[0].split()]
+    out = {}
+    for line in lines[1:1 + nsend]:
+        v = [int(x) for x in line.split()]
+        if len(v) != 2 + v[1]:
+            raise ValueError("%s: malformed target line" % path)
+        out[v[0]] = np.array(v[2:], dtype=np.int64)
+    return out
+
+
+def read_cpu_buff(path):
+    """`buff.k`: "nsend (target count)*" newline "nrecv (source count)*" (GCN-HP/main.cpp:187-209;
+    Parallel-GCN/main.c:456-504). Returns ({target: rows_out}, {source: rows_in})."""
+    l0, l1 = (open(path).read().split("\n") + [""])[:2]
+    a = [int(x) for x in l0.split()]
+    b = [int(x) for x in l1.split()]
+    send = {a[1 + 2 * i]: a[2 + 2 * i] for i in range(a[0])} if a else {}
+    recv = {b[1 + 2 * i]: b[2 + 2 * i] for i in range(b[0])} if b else {}
+    return send, recv
+
+
+def read_cpu_partition(dirpath, k):
+    """Everything `gcnhgp -o dir -k k` wrote, as the inputs of the B200 path: the global adjacency (union of the
+    A.k blocks, scipy COO) and the part vector (from the H.k row lists), plus the parsed conn/buff files so a
+    caller can compare the reference's connectivity with the one the plan builder derives from A.
+    Note: the reference derives `conn` from the OUT-entries of a vertex (owner(i) sends i to owner(j) for A[i][j] != 0,
+    GCN-HP/main.cpp:154-170) — the transpose of what row-wise aggregation needs; the two agree when the pattern
+    is symmetric (which the reference preprocessing produces for symmetric inputs)."""
+    rows, cols, vals, n = [], [], [], None
+    partvec = None
+    conn, buff = [], []
+    for r in range(k):
+        nn, i, j, v = read_cpu_matrix_part(os.path.join(dirpath, "A.%d" % r))
+        n = nn if n is None else n
+        if nn != n:
+            raise ValueError("A.%d: inconsistent n" % r)
+        rows.append(i); cols.append(j); vals.append(v)
+        own = read_cpu_rows_part(os.path.join(dirpath, "H.%d" % r))
+        if partvec is None:
+            partvec = np.full(n, -1, dtype=np.int64)
+        if (partvec[own] != -1).any():
+            raise ValueError("H.%d: a row is owned twice" % r)
+        partvec[own] = r
+        if not np.isin(i, own).all():
+            raise ValueError("A.%d holds rows that H.%d does not list" % (r, r))
+        conn.append(read_cpu_conn(os.path.join(dirpath, "conn.%d" % r)))
+        buff.append(read_cpu_buff(os.path.join(dirpath, "buff.%d" % r)))
+    if (partvec < 0).any():
+        raise ValueError("%d vertices are in no H.k file" % int((partvec < 0).sum()))
+    A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+    return {"A": A, "partvec": partvec, "conn": conn, "buff": buff,
+            "config": read_cpu_config(os.path.join(dirpath, "config"))}
+
+
+# ------------------------------------------------------------------------------------------
 # synthetic graphs
 # ------------------------------------------------------------------------------------------
 
