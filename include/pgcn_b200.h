@@ -114,6 +114,14 @@ int64_t pgcn_plan_get_option(const pgcn_plan* plan, const char* name);
  */
 int pgcn_plan_autotune(pgcn_plan* plan, int32_t f);
 
+/*
+ * Host-only (no GPU needed): the row-block schedule the SpMM walks, for inspection and tests.
+ * rowptr must describe NON-EMPTY rows only (the plan squeezes empty rows out first). Writes up to cap_blocks
+ * blocks as 4 int32 each {first row, nrows | -(slot+1), e_begin, e_end}; returns the number of blocks.
+ */
+int64_t pgcn_debug_schedule(const int32_t* rowptr, int32_t nrows, int64_t edges_per_block, int64_t long_row,
+                            int32_t* blocks_out, int64_t cap_blocks, int32_t* nlong_out, int32_t* nslots_out);
+
 /* Plan-owned device slabs (f_max floats per row), for callers that want zero-copy access:
  * which = 0 send slab (S rows), 1 halo/recv slab (h rows), 2 reverse recv slab (S rows),
  * 3 reverse send slab (h rows: halo partials of A^T g). */

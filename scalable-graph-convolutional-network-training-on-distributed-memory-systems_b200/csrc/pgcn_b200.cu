@@ -235,16 +235,13 @@ void csr_free(DevCsr& c)
 // than `long_row` become ceil(deg/epb) single-row segments with a slot each in the side buffer.
 constexpr int kMaxRowsPerBlock = 128;
 
-int build_schedule(pgcn_plan* p, DevCsr& c)
+// Pure host function (also reachable through pgcn_debug_schedule for CPU-side tests).
+void make_schedule(const int* rp, int nrows_c, int64_t epb, int64_t long_row,
+                   std::vector<int4>& blocks, std::vector<int4>& longs, int& nslots)
 {
-    const int64_t epb = std::max<int64_t>(p->opt_epb, 8);
-    const int64_t long_row = p->opt_long > 0 ? p->opt_long : 4 * epb;
-    if (c.sched_epb == epb && c.sched_long == long_row) return 0;
-
-    std::vector<int4> blocks, longs;
-    blocks.reserve((size_t)(c.nnz / epb + c.nrows_c / kMaxRowsPerBlock + 16));
-    int nslots = 0;
-    const int* rp = c.h_rowptr.data();
+    blocks.clear(); longs.clear(); nslots = 0;
+    const int64_t nnz = nrows_c > 0 ? rp[nrows_c] : 0;
+    blocks.reserve((size_t)(nnz / epb + nrows_c / kMaxRowsPerBlock + 16));
     int cur_begin = 0;         // first row of the open block
     int64_t cur_edges = 0;
     auto close = [&](int row_end) {
@@ -253,7 +250,7 @@ int build_schedule(pgcn_plan* p, DevCsr& c)
         cur_begin = row_end;
         cur_edges = 0;
     };
-    for (int r = 0; r < c.nrows_c; ++r) {
+    for (int r = 0; r < nrows_c; ++r) {
         const int64_t d = (int64_t)rp[r + 1] - rp[r];
         if (d > long_row) {
             close(r);
@@ -272,7 +269,18 @@ int build_schedule(pgcn_plan* p, DevCsr& c)
         cur_edges += d;
         if (r + 1 - cur_begin >= kMaxRowsPerBlock) close(r + 1);
     }
-    close(c.nrows_c);
+    close(nrows_c);
+}
+
+int build_schedule(pgcn_plan* p, DevCsr& c)
+{
+    const int64_t epb = std::max<int64_t>(p->opt_epb, 8);
+    const int64_t long_row = p->opt_long > 0 ? p->opt_long : 4 * epb;
+    if (c.sched_epb == epb && c.sched_long == long_row) return 0;
+
+    std::vector<int4> blocks, longs;
+    int nslots = 0;
+    make_schedule(c.h_rowptr.data(), c.nrows_c, epb, long_row, blocks, longs, nslots);
 
     cudaFree(c.d_blocks); cudaFree(c.d_long); cudaFree(c.d_partial);
     c.d_blocks = nullptr; c.d_long = nullptr; c.d_partial = nullptr;
@@ -650,6 +658,25 @@ int64_t pgcn_plan_get_option(const pgcn_plan* p, const char* name)
     if (n == "blocks_fwd") return p->fwd.nblocks;
     if (n == "long_rows_fwd") return p->fwd.nlong;
     return PGCN_ERR_INVALID;
+}
+
+int64_t pgcn_debug_schedule(const int32_t* rowptr, int32_t nrows, int64_t edges_per_block, int64_t long_row,
+                            int32_t* blocks_out, int64_t cap_blocks, int32_t* nlong_out, int32_t* nslots_out)
+{
+    if (!rowptr || nrows < 0 || edges_per_block < 8) return fail(nullptr, PGCN_ERR_INVALID, "bad schedule arguments");
+    std::vector<int4> blocks, longs;
+    int nslots = 0;
+    make_schedule(rowptr, nrows, edges_per_block, long_row > 0 ? long_row : 4 * edges_per_block, blocks, longs, nslots);
+    if (nlong_out) *nlong_out = (int32_t)longs.size();
+    if (nslots_out) *nslots_out = nslots;
+    if (blocks_out) {
+        const int64_t n = std::min<int64_t>((int64_t)blocks.size(), cap_blocks);
+        for (int64_t i = 0; i < n; ++i) {
+            blocks_out[4 * i] = blocks[i].x; blocks_out[4 * i + 1] = blocks[i].y;
+            blocks_out[4 * i + 2] = blocks[i].z; blocks_out[4 * i + 3] = blocks[i].w;
+        }
+    }
+    return (int64_t)blocks.size();
 }
 
 int pgcn_plan_autotune(pgcn_plan* p, int32_t f)
