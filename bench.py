@@ -128,6 +128,12 @@ def part_vector(args, n, k):
     return graphio.block_partvec(n, k), "block (contiguous vertex ranges)"
 
 
+def thread_candidates(ncpu):
+    """Thread counts tried for the CPU arm (the best one is reported): all logical CPUs down to 1/8 of them —
+    SMT siblings and container CPU quotas often make fewer threads faster for this bandwidth/latency-bound loop."""
+    return sorted({max(1, ncpu), max(1, ncpu // 2), max(1, ncpu // 4), max(1, ncpu // 8)})
+
+
 def cpu_baseline(lp, f, budget_s=20.0):
     """C/OpenMP restatement of the GraphBLAS aggregation on this host's cores, same rank data."""
     from oracle import build_oracle
@@ -137,7 +143,7 @@ def cpu_baseline(lp, f, budget_s=20.0):
     build_oracle.spmm_csr(lp.rowptr, lp.colidx, lp.vals, H, lp.m, out=out)       # warm-up / page-in
     ncpu = os.cpu_count() or 1
     build_oracle.best_thread_count(lambda: build_oracle.spmm_csr(lp.rowptr, lp.colidx, lp.vals, H, lp.m, out=out),
-                                   sorted({ncpu, max(1, ncpu // 2)}))
+                                   thread_candidates(ncpu))
     times = []
     t_all = time.perf_counter()
     while len(times) < 3 or (time.perf_counter() - t_all < budget_s and len(times) < 50):
@@ -166,7 +172,7 @@ def run_reference(args):
     out = np.empty((n, f), dtype=np.float32)
     ncpu = os.cpu_count() or 1
     build_oracle.best_thread_count(lambda: build_oracle.spmm_csr(lp.rowptr, lp.colidx, lp.vals, H, n, out=out),
-                                   sorted({ncpu, max(1, ncpu // 2)}))
+                                   thread_candidates(ncpu))
     for _ in range(max(args.warmup, 1)):
         build_oracle.spmm_csr(lp.rowptr, lp.colidx, lp.vals, H, n, out=out)
     t0 = time.perf_counter()
