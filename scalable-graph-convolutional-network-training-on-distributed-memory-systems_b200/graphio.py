@@ -173,10 +173,14 @@ def rmat_edges(n, n_undirected, abcd=(0.57, 0.19, 0.19, 0.05), seed=1, permute=T
         ok = (u < n) & (v < n) & (u != v)
         u, v = u[ok], v[ok]
         lo, hi = np.minimum(u, v), np.maximum(u, v)
+        before = keys.shape[0]
         keys = np.unique(np.concatenate([keys, lo * n + hi]))
         if keys.shape[0] >= want:
             break
-        draw = int((want - keys.shape[0]) * 1.5) + 1024
+        # next round: size the draw by the acceptance rate just observed (dense, skewed graphs such as the
+        # Reddit-shaped C4 reject most draws as duplicates once the hub neighbourhoods fill up)
+        accept = max((keys.shape[0] - before) / float(draw), 0.02)
+        draw = int(min((want - keys.shape[0]) / accept * 1.3 + 1024, 4.0e8))
     if keys.shape[0] > want:
         keys = keys[np.sort(rng.permutation(keys.shape[0])[:want])]
     lo, hi = keys // n, keys % n
