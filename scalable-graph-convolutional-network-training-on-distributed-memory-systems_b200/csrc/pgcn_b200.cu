@@ -7,6 +7,7 @@
 // peer-memory path that stores rows directly into the neighbour GPU's slab over NVLink).
 #include "../../include/pgcn_b200.h"
 #include "spmm_kernels.cuh"
+#include "spmm_ring.cuh"
 
 #include <dlfcn.h>
 #include <algorithm>
@@ -75,19 +76,22 @@ struct DevCsr {
     int nrows_c = 0;                // non-empty rows = rows the schedule walks
     int64_t nnz = 0;
     std::vector<int> h_rowptr;      // COMPACT row pointers (empty rows squeezed out), for scheduling
-    int* d_colflag = nullptr;       // column | kLastFlag on the last entry of each row
-    float* d_vals = nullptr;
+    int2* d_cw = nullptr;           // {column | kLastFlag on the last entry of each row | kColdFlag, value bits},
+                                    // padded with zero pairs to a multiple of 32 entries (256-byte bulk-copy pieces)
     int* d_rowids = nullptr;        // compact row -> output row, null when the identity
     int* d_empty = nullptr;         // output rows without entries (zero-filled when beta == 0)
     int nempty = 0;
-    // schedule
-    int4* d_blocks = nullptr;
-    int nblocks = 0;
-    int4* d_long = nullptr;
-    int nlong = 0;
-    int nslots = 0;
-    float* d_partial = nullptr;
-    int64_t sched_epb = -1, sched_long = -1;
+    // schedules: [0] register-pipeline kernel (small row blocks, one per lane group),
+    //            [1] shared-memory ring kernel (large row blocks, one per warp)
+    struct Sched {
+        int4* d_blocks = nullptr;
+        int nblocks = 0;
+        int4* d_long = nullptr;
+        int nlong = 0;
+        int nslots = 0;
+        float* d_partial = nullptr;
+        int64_t epb = -1, long_row = -1;
+    } sched[2];
 };
 
 struct P2PBlob {                     // what pgcn_p2p_export writes (PGCN_P2P_HANDLE_BYTES)
@@ -123,6 +127,14 @@ struct pgcn_plan {
 
     // options
     int64_t opt_epb = 128, opt_long = 0, opt_tile = 0, opt_overlap = 1, opt_hot_mb = 64;
+    // kernel: 0 auto (ring with TMA bulk copies where it applies), 4 register pipeline, 5 ring/1-D TMA,
+    //         6 ring/cp.async, 7 ring/TMA tile::gather4
+    int64_t opt_g4_box = 1;
+    int64_t opt_kernel = 0, opt_ring_slots = 32, opt_ring_epb = 1024, opt_ring_long = 0, opt_persistent = 0;
+    bool ring_attr_set[12] = {false};
+    int ring_ctas_per_sm[12] = {0};
+    unsigned int* d_counter = nullptr;     // block counters of the persistent ring kernel (one per feature tile)
+    int num_sms = 148;
 
     // NCCL
     ncclComm_t comm = nullptr;
@@ -193,17 +205,21 @@ int csr_upload(pgcn_plan* p, DevCsr& c, int nrows, const int* rowptr, const int*
 {
     c.nrows = nrows;
     c.nnz = rowptr[nrows];
-    std::vector<int> colflag(colidx, colidx + c.nnz);
-    if (col_refs && cold_thresh >= 0) {
-        for (int64_t e = 0; e < c.nnz; ++e)
-            if (col_refs[colidx[e]] <= cold_thresh) colflag[e] |= kColdFlag;
+    std::vector<int2> cw((size_t)((c.nnz + 31) / 32 * 32 + 32), make_int2(0, 0));
+    for (int64_t e = 0; e < c.nnz; ++e) {
+        int cf = colidx[e];
+        if (col_refs && cold_thresh >= 0 && col_refs[colidx[e]] <= cold_thresh) cf |= kColdFlag;
+        float v = vals[e];
+        int vb;
+        memcpy(&vb, &v, 4);
+        cw[(size_t)e] = make_int2(cf, vb);
     }
     std::vector<int> rowids, empty;
     c.h_rowptr.clear();
     c.h_rowptr.push_back(0);
     for (int r = 0; r < nrows; ++r) {
         if (rowptr[r + 1] > rowptr[r]) {
-            colflag[(size_t)rowptr[r + 1] - 1] |= kLastFlag;
+            cw[(size_t)rowptr[r + 1] - 1].x |= kLastFlag;
             c.h_rowptr.push_back(rowptr[r + 1]);
             rowids.push_back(ext_rowmap ? (*ext_rowmap)[r] : r);
         } else if (!ext_rowmap) {
@@ -213,8 +229,7 @@ int csr_upload(pgcn_plan* p, DevCsr& c, int nrows, const int* rowptr, const int*
     c.nrows_c = (int)rowids.size();
     c.nempty = (int)empty.size();
     int rc;
-    if ((rc = upload(p, &c.d_colflag, colflag.data(), (size_t)c.nnz))) return rc;
-    if ((rc = upload(p, &c.d_vals, vals, (size_t)c.nnz))) return rc;
+    if ((rc = upload(p, &c.d_cw, cw.data(), cw.size()))) return rc;
     if (ext_rowmap || c.nempty > 0) {
         if ((rc = upload(p, &c.d_rowids, rowids.data(), rowids.size()))) return rc;
     }
@@ -226,8 +241,8 @@ int csr_upload(pgcn_plan* p, DevCsr& c, int nrows, const int* rowptr, const int*
 
 void csr_free(DevCsr& c)
 {
-    cudaFree(c.d_colflag); cudaFree(c.d_vals); cudaFree(c.d_rowids); cudaFree(c.d_empty);
-    cudaFree(c.d_blocks); cudaFree(c.d_long); cudaFree(c.d_partial);
+    cudaFree(c.d_cw); cudaFree(c.d_rowids); cudaFree(c.d_empty);
+    for (auto& sc : c.sched) { cudaFree(sc.d_blocks); cudaFree(sc.d_long); cudaFree(sc.d_partial); }
     c = DevCsr();
 }
 
@@ -237,7 +252,8 @@ constexpr int kMaxRowsPerBlock = 128;
 
 // Pure host function (also reachable through pgcn_debug_schedule for CPU-side tests).
 void make_schedule(const int* rp, int nrows_c, int64_t epb, int64_t long_row,
-                   std::vector<int4>& blocks, std::vector<int4>& longs, int& nslots)
+                   std::vector<int4>& blocks, std::vector<int4>& longs, int& nslots,
+                   int max_rows = kMaxRowsPerBlock)
 {
     blocks.clear(); longs.clear(); nslots = 0;
     const int64_t nnz = nrows_c > 0 ? rp[nrows_c] : 0;
@@ -267,32 +283,32 @@ void make_schedule(const int* rp, int nrows_c, int64_t epb, int64_t long_row,
         }
         if (cur_edges > 0 && cur_edges + d > epb) close(r);
         cur_edges += d;
-        if (r + 1 - cur_begin >= kMaxRowsPerBlock) close(r + 1);
+        if (r + 1 - cur_begin >= max_rows) close(r + 1);
     }
     close(nrows_c);
 }
 
-int build_schedule(pgcn_plan* p, DevCsr& c)
+int build_schedule(pgcn_plan* p, DevCsr& c, int which, int64_t epb, int64_t long_row)
 {
-    const int64_t epb = std::max<int64_t>(p->opt_epb, 8);
-    const int64_t long_row = p->opt_long > 0 ? p->opt_long : 4 * epb;
-    if (c.sched_epb == epb && c.sched_long == long_row) return 0;
+    DevCsr::Sched& sc = c.sched[which];
+    if (sc.epb == epb && sc.long_row == long_row) return 0;
 
     std::vector<int4> blocks, longs;
     int nslots = 0;
-    make_schedule(c.h_rowptr.data(), c.nrows_c, epb, long_row, blocks, longs, nslots);
+    make_schedule(c.h_rowptr.data(), c.nrows_c, epb, long_row, blocks, longs, nslots,
+                  which == 1 ? (1 << 30) : kMaxRowsPerBlock);
 
-    cudaFree(c.d_blocks); cudaFree(c.d_long); cudaFree(c.d_partial);
-    c.d_blocks = nullptr; c.d_long = nullptr; c.d_partial = nullptr;
+    cudaFree(sc.d_blocks); cudaFree(sc.d_long); cudaFree(sc.d_partial);
+    sc.d_blocks = nullptr; sc.d_long = nullptr; sc.d_partial = nullptr;
     int rc;
-    if ((rc = upload(p, &c.d_blocks, blocks.data(), blocks.size()))) return rc;
-    if ((rc = upload(p, &c.d_long, longs.data(), longs.size()))) return rc;
-    CU(p, cudaMalloc((void**)&c.d_partial, std::max<size_t>((size_t)nslots * p->f_max, 1) * sizeof(float)));
-    c.nblocks = (int)blocks.size();
-    c.nlong = (int)longs.size();
-    c.nslots = nslots;
-    c.sched_epb = epb;
-    c.sched_long = long_row;
+    if ((rc = upload(p, &sc.d_blocks, blocks.data(), blocks.size()))) return rc;
+    if ((rc = upload(p, &sc.d_long, longs.data(), longs.size()))) return rc;
+    CU(p, cudaMalloc((void**)&sc.d_partial, std::max<size_t>((size_t)nslots * p->f_max, 1) * sizeof(float)));
+    sc.nblocks = (int)blocks.size();
+    sc.nlong = (int)longs.size();
+    sc.nslots = nslots;
+    sc.epb = epb;
+    sc.long_row = long_row;
     return 0;
 }
 
@@ -340,12 +356,83 @@ spmm_fn pick_lpe(int lpe, int vpl, bool halo)
     }
 }
 
+typedef void (*ring_fn)(const SpmmArgs, const RingArgs);
+typedef void (*ring_g4_fn)(const SpmmArgs, const RingArgs, const CUtensorMap, const CUtensorMap);
+
+// cuTensorMapEncodeTiled, resolved through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_fn g_encode_tiled = nullptr;
+bool g_encode_tried = false;
+
+encode_tiled_fn encode_tiled()
+{
+    if (!g_encode_tried) {
+        g_encode_tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            g_encode_tiled = reinterpret_cast<encode_tiled_fn>(fn);
+        else
+            cudaGetLastError();
+    }
+    return g_encode_tiled;
+}
+
+// Tensor map of a row-major fp32 matrix [rows, f] for tile::gather4 loads of `tile` floats per row.
+bool make_row_map(CUtensorMap* tm, const float* base, int64_t rows, int f, int tile, int box_rows)
+{
+    encode_tiled_fn enc = encode_tiled();
+    if (!enc || !base) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)f, (cuuint64_t)std::max<int64_t>(rows, 1)};
+    const cuuint64_t gstride[1] = {(cuuint64_t)f * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)tile, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int VPL, int MODE>
+ring_fn pick_ring_ns(int ns)
+{
+    return ns == 16 ? spmm_ring_kernel<VPL, 16, MODE> : spmm_ring_kernel<VPL, 32, MODE>;
+}
+
+ring_fn pick_ring(int vpl, int ns, int mode)
+{
+    if (vpl == 2) return mode ? pick_ring_ns<2, 1>(ns) : pick_ring_ns<2, 0>(ns);
+    return mode ? pick_ring_ns<1, 1>(ns) : pick_ring_ns<1, 0>(ns);
+}
+
+bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
+// Which SpMM kernel serves width f with these operands: the shared-memory ring (TMA bulk copies) needs whole
+// 128-float vectors and 16-byte aligned rows; everything else takes the register pipeline.
+bool use_ring(const pgcn_plan* p, const float* H0, const float* H1, int f)
+{
+    if (p->opt_kernel == 4) return false;
+    return f % 128 == 0 && aligned16(H0) && aligned16(H1);
+}
+
 int launch_spmm(pgcn_plan* p, DevCsr& c, const float* H0, const float* H1, int split,
                 float* Z0, float* Z1, int zsplit, int f, int beta, cudaStream_t st)
 {
     if (c.nrows == 0) return 0;
-    int rc = build_schedule(p, c);
+    const bool ring = use_ring(p, H0, H1, f) && aligned16(Z0) && aligned16(Z1);
+    int64_t epb, long_row;
+    if (ring) {
+        epb = std::max<int64_t>(p->opt_ring_epb, 64);
+        long_row = p->opt_ring_long > 0 ? p->opt_ring_long : 2 * epb;
+    } else {
+        epb = std::max<int64_t>(p->opt_epb, 8);
+        long_row = p->opt_long > 0 ? p->opt_long : 4 * epb;
+    }
+    int rc = build_schedule(p, c, ring ? 1 : 0, epb, long_row);
     if (rc) return rc;
+    const DevCsr::Sched& sc = c.sched[ring ? 1 : 0];
     const TileCfg t = choose_tile(p, f);
     if (c.nempty > 0 && !beta) {
         ZeroArgs za;
@@ -357,26 +444,69 @@ int launch_spmm(pgcn_plan* p, DevCsr& c, const float* H0, const float* H1, int s
         ++p->launches;
     }
     SpmmArgs a;
-    a.blocks = c.d_blocks; a.nblocks = c.nblocks;
-    a.colflag = c.d_colflag; a.vals = c.d_vals;
+    a.blocks = sc.d_blocks; a.nblocks = sc.nblocks;
+    a.cw = c.d_cw;
     a.H0 = H0; a.H1 = H1; a.split = split;
     a.Z0 = Z0; a.Z1 = Z1; a.zsplit = zsplit;
     a.rowids = c.d_rowids;
-    a.partial = c.d_partial; a.f = f; a.beta = beta;
-    if (c.nblocks > 0) {
+    a.partial = sc.d_partial; a.f = f; a.beta = beta;
+    if (sc.nblocks > 0 && ring) {
+        const int vpl = (f % 256 == 0) ? 2 : 1;
+        const int tiles = f / (128 * vpl);
+        int ns = (int)p->opt_ring_slots;
+        if (ns != 16) ns = 32;
+        int mode = p->opt_kernel == 6 ? 1 : (p->opt_kernel == 7 ? 2 : 0);
+        CUtensorMap tm0, tm1;
+        if (mode == 2) {
+            // H0 holds the columns below `split` (all of them when there is no halo slab), H1 the rest
+            const int tile = 128 * vpl;
+            const int box_rows = (int)p->opt_g4_box;
+            bool ok = make_row_map(&tm0, H0, 1 << 30, f, tile, box_rows);
+            if (ok && H1) ok = make_row_map(&tm1, H1, 1 << 30, f, tile, box_rows);
+            else if (ok) tm1 = tm0;
+            if (!ok) mode = 0;                                   // no driver entry point: 1-D bulk copies
+        }
+        ring_fn fn = mode == 2 ? nullptr : pick_ring(vpl, ns, mode);
+        ring_g4_fn fn4 = nullptr;
+        if (mode == 2)
+            fn4 = vpl == 2 ? (ns == 16 ? spmm_ring_g4_kernel<2, 16> : spmm_ring_g4_kernel<2, 32>)
+                           : (ns == 16 ? spmm_ring_g4_kernel<1, 16> : spmm_ring_g4_kernel<1, 32>);
+        const void* fptr = mode == 2 ? (const void*)fn4 : (const void*)fn;
+        const size_t smem = ring_smem_bytes(vpl, ns);
+        // opt-in to > 48 KB of dynamic shared memory, once per kernel instance
+        const int slot = ((vpl - 1) * 2 + (ns == 16 ? 0 : 1)) * 3 + mode;
+        if (!p->ring_attr_set[slot]) {
+            CU(p, cudaFuncSetAttribute(fptr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int nb = 0;
+            CU(p, cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&nb, fptr, kRingWarps * 32, smem, 0));
+            p->ring_ctas_per_sm[slot] = std::max(nb, 1);
+            p->ring_attr_set[slot] = true;
+        }
+        RingArgs ra;
+        ra.counter = nullptr; ra.hub = nullptr; ra.nhub = 0;
+        dim3 grid((unsigned)((sc.nblocks + kRingWarps - 1) / kRingWarps), (unsigned)tiles);
+        if (p->opt_persistent) {
+            CU(p, cudaMemsetAsync(p->d_counter, 0, 64 * sizeof(unsigned int), st));
+            ra.counter = p->d_counter;
+            grid.x = std::min<unsigned>(grid.x, (unsigned)(p->num_sms * p->ring_ctas_per_sm[slot]));
+        }
+        if (mode == 2) fn4<<<grid, kRingWarps * 32, smem, st>>>(a, ra, tm0, tm1);
+        else fn<<<grid, kRingWarps * 32, smem, st>>>(a, ra);
+        ++p->launches;
+    } else if (sc.nblocks > 0) {
         const int groups_per_cta = kSpmmThreads / t.lpe;
-        dim3 grid((unsigned)((c.nblocks + groups_per_cta - 1) / groups_per_cta), (unsigned)t.tiles);
+        dim3 grid((unsigned)((sc.nblocks + groups_per_cta - 1) / groups_per_cta), (unsigned)t.tiles);
         const bool halo = (H1 != nullptr);
         spmm_fn fn = (t.vw == 4) ? pick_lpe<4>(t.lpe, t.vpl, halo) : pick_lpe<1>(t.lpe, t.vpl, halo);
         fn<<<grid, kSpmmThreads, 0, st>>>(a);
         ++p->launches;
     }
-    if (c.nlong > 0) {
+    if (sc.nlong > 0) {
         FixupArgs fa;
-        fa.long_rows = c.d_long; fa.nlong = c.nlong; fa.partial = c.d_partial;
+        fa.long_rows = sc.d_long; fa.nlong = sc.nlong; fa.partial = sc.d_partial;
         fa.Z0 = Z0; fa.Z1 = Z1; fa.zsplit = zsplit; fa.rowids = c.d_rowids; fa.f = f; fa.beta = beta;
         const int nvec = f / t.vw;
-        const unsigned grid = (unsigned)c.nlong * (unsigned)((nvec + 31) / 32);
+        const unsigned grid = (unsigned)sc.nlong * (unsigned)((nvec + 31) / 32);
         if (t.vw == 4) spmm_fixup_kernel<4><<<grid, 32 * kFixupGroups, 0, st>>>(fa);
         else spmm_fixup_kernel<1><<<grid, 32 * kFixupGroups, 0, st>>>(fa);
         ++p->launches;
@@ -404,8 +534,10 @@ int launch_pack(pgcn_plan* p, const float* H, float* slab, float* const* peer_ds
     PackArgs a;
     a.send_idx = p->d_send_idx; a.S = p->S; a.H = H; a.slab = slab; a.k = p->k; a.f = f;
     a.to_peers = peer_dst != nullptr;
-    for (int i = 0; i <= p->k; ++i) a.send_off[i] = p->send_off[i];
-    for (int i = 0; i < p->k; ++i) a.peer_dst[i] = peer_dst ? peer_dst[i] : nullptr;
+    if (a.to_peers) {                                     // peer transport: k <= kMaxPeersDev (pgcn_p2p_export)
+        for (int i = 0; i <= p->k; ++i) a.send_off[i] = p->send_off[i];
+        for (int i = 0; i < p->k; ++i) a.peer_dst[i] = peer_dst[i];
+    }
     const int vw = (f % 4 == 0) ? 4 : 1;
     const unsigned grid = grid_for(p->S * (f / vw));
     if (vw == 4) pack_rows_kernel<4><<<grid, 256, 0, st>>>(a);
@@ -568,6 +700,12 @@ int pgcn_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* 
         p->have_split = true;
     }
 
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, p->device) == cudaSuccess) p->num_sms = prop.multiProcessorCount;
+        std::vector<unsigned int> zeros(64, 0u);
+        TRY(upload(p, &p->d_counter, zeros.data(), zeros.size()));
+    }
     TRY(upload(p, &p->d_send_idx, send_idx, (size_t)S));
     // boundary CSR: for every owned row that appears in some send list, the slab positions
     {
@@ -621,7 +759,7 @@ int pgcn_plan_destroy(pgcn_plan* p)
     cudaFree(p->d_send_idx);
     cudaFree(p->d_brow); cudaFree(p->d_bptr); cudaFree(p->d_bpos);
     cudaFree(p->d_send_slab); cudaFree(p->d_halo_slab); cudaFree(p->d_rrecv_slab); cudaFree(p->d_hsend_slab);
-    cudaFree(p->d_hostH); cudaFree(p->d_hostZ);
+    cudaFree(p->d_hostH); cudaFree(p->d_hostZ); cudaFree(p->d_counter);
     if (p->comm_stream) cudaStreamDestroy(p->comm_stream);
     if (p->host_stream) cudaStreamDestroy(p->host_stream);
     if (p->ev_a) cudaEventDestroy(p->ev_a);
@@ -636,6 +774,12 @@ int pgcn_plan_set_option(pgcn_plan* p, const char* name, int64_t value)
     if (!p || !name) return fail(p, PGCN_ERR_INVALID, "null argument");
     const std::string n(name);
     if (n == "edges_per_block") p->opt_epb = value;
+    else if (n == "kernel") p->opt_kernel = value;
+    else if (n == "ring_slots") p->opt_ring_slots = value;
+    else if (n == "ring_edges_per_block") p->opt_ring_epb = value;
+    else if (n == "ring_long_row") p->opt_ring_long = value;
+    else if (n == "persistent") p->opt_persistent = value;
+    else if (n == "g4_box_rows") p->opt_g4_box = value;
     else if (n == "long_row") p->opt_long = value;
     else if (n == "tile_floats") p->opt_tile = value;
     else if (n == "hot_mb") p->opt_hot_mb = value;
@@ -649,14 +793,21 @@ int64_t pgcn_plan_get_option(const pgcn_plan* p, const char* name)
     if (!p || !name) return PGCN_ERR_INVALID;
     const std::string n(name);
     if (n == "edges_per_block") return p->opt_epb;
+    if (n == "kernel") return p->opt_kernel;
+    if (n == "ring_slots") return p->opt_ring_slots;
+    if (n == "ring_edges_per_block") return p->opt_ring_epb;
+    if (n == "ring_long_row") return p->opt_ring_long;
+    if (n == "persistent") return p->opt_persistent;
     if (n == "long_row") return p->opt_long;
     if (n == "tile_floats") return p->opt_tile;
     if (n == "hot_mb") return p->opt_hot_mb;
     if (n == "overlap") return p->opt_overlap;
     if (n == "p2p") return p->p2p ? 1 : 0;
     if (n == "nccl") return p->comm ? 1 : 0;
-    if (n == "blocks_fwd") return p->fwd.nblocks;
-    if (n == "long_rows_fwd") return p->fwd.nlong;
+    if (n == "blocks_fwd") return p->fwd.sched[0].nblocks;
+    if (n == "long_rows_fwd") return p->fwd.sched[0].nlong;
+    if (n == "ring_blocks_fwd") return p->fwd.sched[1].nblocks;
+    if (n == "ring_long_rows_fwd") return p->fwd.sched[1].nlong;
     return PGCN_ERR_INVALID;
 }
 

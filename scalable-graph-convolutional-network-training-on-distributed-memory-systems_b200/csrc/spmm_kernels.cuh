@@ -45,8 +45,8 @@ constexpr int kColMask = 0x3fffffff;
 struct SpmmArgs {
     const int4* blocks;      // {first row (compact id), nrows | -(slot+1), e_begin, e_end}
     int nblocks;
-    const int* colflag;      // column index | kLastFlag on the last entry of each (non-empty) row
-    const float* vals;
+    const int2* cw;          // per stored entry {column | flags, value bits}; kLastFlag on the last entry of
+                             // each (non-empty) row; padded to a multiple of 32 entries (bulk-copy pieces)
     const float* H0;         // columns [0, split)
     const float* H1;         // columns [split, ...)   (halo slab), may be null when unused
     int split;
@@ -116,8 +116,7 @@ __device__ __forceinline__ float ld_feat_hint(const float* p, unsigned long long
     return r;
 }
 // column indices / values: touched once -> streaming, do not displace H rows.
-__device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
-__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ int2 ld_stream(const int2* p) { return __ldcs(p); }
 // outputs: written once -> streaming stores.
 __device__ __forceinline__ void st_out(float4* p, const float4& v) { __stcs(p, v); }
 __device__ __forceinline__ void st_out(float* p, const float& v) { __stcs(p, v); }
@@ -239,14 +238,11 @@ spmm_rowblock_kernel(const SpmmArgs a)
     int buf = 0;
     {
         int2 cw = make_int2(0, 0);
-        if (e + gl < e_end) { cw.x = ld_stream(a.colflag + e + gl); cw.y = __float_as_int(ld_stream(a.vals + e + gl)); }
+        if (e + gl < e_end) cw = ld_stream(a.cw + e + gl);
         s_cw[0][threadIdx.x] = cw;
     }
     int2 cw_next = make_int2(0, 0);
-    if (e + LPE + gl < e_end) {
-        cw_next.x = ld_stream(a.colflag + e + LPE + gl);
-        cw_next.y = __float_as_int(ld_stream(a.vals + e + LPE + gl));
-    }
+    if (e + LPE + gl < e_end) cw_next = ld_stream(a.cw + e + LPE + gl);
     __syncwarp(gmask);
 
     while (e < e_end) {
@@ -287,10 +283,7 @@ spmm_rowblock_kernel(const SpmmArgs a)
         buf ^= 1;
         s_cw[buf][threadIdx.x] = cw_next;
         cw_next = make_int2(0, 0);
-        if (e + LPE + gl < e_end) {
-            cw_next.x = ld_stream(a.colflag + e + LPE + gl);
-            cw_next.y = __float_as_int(ld_stream(a.vals + e + LPE + gl));
-        }
+        if (e + LPE + gl < e_end) cw_next = ld_stream(a.cw + e + LPE + gl);
         __syncwarp(gmask);
     }
 

@@ -1,0 +1,376 @@
+// spmm_ring.cuh — the Blackwell-native SpMM of the PGCN aggregation path: gathered H rows are staged
+// ASYNCHRONOUSLY in shared memory (1-D TMA bulk copies, cp.async.bulk + mbarrier complete_tx), the
+// segmented FMA runs out of shared memory.
+//
+// Replaces torch.sparse.mm(A, H) / torch.sparse.mm(A.t(), g) of GPU/PGCN.py:127,132 for feature widths
+// that are multiples of 128 floats (the benchmark widths 128 and 256); other widths take the register
+// pipeline of spmm_kernels.cuh.
+//
+// Why: the register-buffered gather of spmm_rowblock_kernel keeps bytes-in-flight in REGISTERS (2 rows per
+// warp x 48 warps), spends ~35 issue slots per edge and is capped by occupancy. Here
+//   * every WARP owns a private ring of NS row slots (NS x f x 4 bytes of shared memory) and a small ring
+//     of index pieces; nothing is shared between warps, so there is no CTA-level synchronisation at all;
+//   * lanes 0..G-1 each issue ONE bulk copy (UBLKCP) of a whole H row (512 B at f = 128) per group of G
+//     edges; the group's mbarrier completes when all G rows have landed (expect_tx = G x row bytes);
+//   * the (column|flags, value) stream is fetched the same way in 256-byte pieces of 32 entries, so the
+//     kernel issues no ordinary global loads at all on its hot path;
+//   * consumption is one broadcast LDS.64 (index pair) + one conflict-free LDS.128 per edge and lane,
+//     4 FFMA, a row-end test; bytes in flight per SM = warps x NS x row bytes (e.g. 12 x 32 x 512 B =
+//     192 KB) instead of 48 KB, at ~10 issue slots per edge.
+//   * MODE 1 is the same ring filled with per-lane 16-byte cp.async (LDGSTS) copies — kept for comparison.
+// Row blocks come from the same host schedule as the register kernel (rows cut into blocks of about
+// edges_per_block entries, long rows split into single-row segments that the fixup kernel sums in a fixed
+// order), one block per warp; with `counter` set, the CTAs are persistent and warps fetch blocks dynamically.
+#pragma once
+#include <cuda.h>
+#include "spmm_kernels.cuh"
+
+namespace pgcn {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier; L2 eviction policy per copy.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                         unsigned long long pol)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+// 2-D tensor-map TMA in tile::gather4 mode: FOUR arbitrary rows of H (row indices r0..r3, column offset x) land as
+// four consecutive row slots in shared memory with ONE instruction (UTMALDG.2D.GATHER4).
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tm, int x, int r0, int r1, int r2, int r3,
+                                            uint32_t bar, unsigned long long pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;"
+        ::"r"(dst), "l"(tm), "r"(x), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, unsigned long long pol)
+{
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One call site per row end would replicate the store sequence 32+ times in the unrolled consumer; keeping it
+// out of line keeps the hot loop inside the instruction cache (the rows-end path runs once per ~17 edges).
+template <int VPL>
+__device__ __noinline__ void ring_store_row(float4 a0, float4 a1, const int* rowids, int row, float* Z0, float* Z1,
+                                            int zsplit, size_t pitch, size_t off, int beta)
+{
+    const int orow = (rowids != nullptr) ? __ldg(rowids + row) : row;
+    char* zb = (orow < zsplit) ? reinterpret_cast<char*>(Z0) + (size_t)(unsigned)orow * pitch
+                               : reinterpret_cast<char*>(Z1) + (size_t)(unsigned)(orow - zsplit) * pitch;
+    zb += off;
+    float4* zp = reinterpret_cast<float4*>(zb);
+    if (beta) vadd(a0, *zp);
+    st_out(zp, a0);
+    if (VPL == 2) {
+        float4* zq = reinterpret_cast<float4*>(zb + 512);
+        if (beta) vadd(a1, *zq);
+        st_out(zq, a1);
+    }
+}
+
+constexpr int kRingWarps = 4;        // warps per CTA (each fully independent)
+constexpr int kRingG = 8;            // edges per completion group (= 1/4 of an index piece)
+constexpr int kRingPieces = 4;       // index pieces (32 entries = 256 B each) per warp
+
+struct RingArgs {
+    unsigned int* counter;   // null: block = blockIdx.x * kRingWarps + warp; else dynamic (persistent CTAs)
+    const float* hub;        // reserved (hub rows resident in shared memory)
+    int nhub;
+};
+
+// per warp: NS row slots | NP index pieces | NS weights | NG + NP mbarriers
+__host__ __device__ constexpr size_t ring_warp_bytes(int vpl, int ns)
+{
+    return ((size_t)ns * vpl * 512 + (size_t)kRingPieces * 256 + (size_t)ns * 4 +
+            (size_t)(ns / kRingG + kRingPieces) * 8 + 127) / 128 * 128;
+}
+__host__ __device__ constexpr size_t ring_smem_bytes(int vpl, int ns) { return ring_warp_bytes(vpl, ns) * kRingWarps + 128; }
+
+// VPL: 128-float vector groups per row (tile of f); NS: row slots per warp (16 or 32);
+// MODE 0: 1-D TMA bulk copies (UBLKCP + mbarrier), 1: per-lane 16-byte cp.async (LDGSTS + wait_group),
+// MODE 2: 2-D tensor-map TMA in tile::gather4 mode (UTMALDG.2D.GATHER4, four rows per instruction; groups that
+//         mix own and halo columns, or are cut by a block boundary, fall back to the 1-D copies of MODE 0).
+//
+// The edge stream is walked in GLOBALLY ALIGNED units: a piece = entries [32 P, 32 P + 32) of the pair array (one
+// 256-byte bulk copy), a group = entries [8 g, 8 g + 8) (one completion unit of the row ring, slot group g % NG).
+// A row block [e0, e1) starts and ends anywhere; entries of its first / last group outside the block are masked.
+// Because everything is aligned, the loop body is one piece = four groups with STATIC slot numbers: consume group
+// (P, q), then issue the group NG positions ahead into the slots just freed. What travels from issue to
+// consumption lives in registers (row-end mask, valid mask per slot group) and in a tiny weight array.
+template <int VPL, int NS, int MODE>
+__device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra, const CUtensorMap* tm0, const CUtensorMap* tm1)
+{
+    constexpr int G = kRingG, NG = NS / G, NP = kRingPieces;
+    constexpr uint32_t RB = VPL * 512;                                   // bytes of one row tile
+    static_assert(NG == 2 || NG == 4, "ring holds 2 or 4 groups of 8 rows");
+    extern __shared__ __align__(128) unsigned char ring_smem[];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wbase = ring_smem + (size_t)warp * ring_warp_bytes(VPL, NS);
+    const uint32_t s_data = smem_u32(wbase);                             // NS slots of RB bytes
+    const uint32_t s_idx = s_data + NS * RB;                             // NP pieces of 32 int2
+    const uint32_t s_gbar = s_idx + NP * 256 + NS * 4;                   // NG group barriers
+    const uint32_t s_pbar = s_gbar + NG * 8;                             // NP piece barriers
+    const int2* idx_gen = reinterpret_cast<const int2*>(wbase + (size_t)NS * RB);
+    float* w_slot = reinterpret_cast<float*>(wbase + (size_t)NS * RB + NP * 256);   // weight of the edge in each slot
+    const float4* data_gen = reinterpret_cast<const float4*>(wbase) + lane;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NG + NP; ++i) mbar_init(s_gbar + i * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    const unsigned long long pol_hot = l2_policy_evict_last();
+    const unsigned long long pol_cold = l2_policy_evict_first();
+    // blockIdx.y walks feature tiles of 128 * VPL floats (f = 384, 512, ...): row pitch f * 4, tile offset y * RB
+    const size_t pitch = (size_t)a.f * 4;
+    const size_t toff = (size_t)blockIdx.y * RB;
+    const char* hb0 = reinterpret_cast<const char*>(a.H0) + toff;
+    const char* hb1 = reinterpret_cast<const char*>(a.H1) + toff - (size_t)a.split * pitch;   // halo slab, column-relative
+    const unsigned usplit = a.H1 ? (unsigned)a.split : 0xffffffffu;
+    unsigned int* counter = ra.counter ? ra.counter + blockIdx.y : nullptr;
+
+    uint32_t gpar = 0;                   // phase parity of each group barrier (bit sg)
+    uint32_t pfetch = 0, pwait = 0;      // pieces fetched / waited for by this warp so far (FIFO through NP slots)
+
+    float4 acc[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    int blk = counter ? 0 : (int)(blockIdx.x * kRingWarps + warp);
+    if (counter) {
+        if (lane == 0) blk = (int)atomicAdd(counter, 1u);
+        blk = __shfl_sync(0xffffffffu, blk, 0);
+    }
+
+    while (blk < a.nblocks) {
+        const int4 b = __ldg(a.blocks + blk);
+        const bool seg = b.y < 0;
+        const int lastmask = seg ? 0 : kLastFlag;
+        const int e0 = b.z, e1 = b.w;
+        int row = b.x;
+        const int gA = e0 >> 3, gB = (e1 - 1) >> 3;                      // first / last (aligned) group
+        const int P0 = gA >> 2, P1 = gB >> 2;                            // first / last piece
+        uint32_t vmask[NG], emask[NG];                                   // per slot group: valid edges, row ends
+#pragma unroll
+        for (int i = 0; i < NG; ++i) vmask[i] = emask[i] = 0;
+        int pnext = P0;                                                  // next piece to fetch
+        uint32_t pslot = pwait % NP;                                     // ring slot of the piece being issued from
+
+        auto fetch_piece = [&]() {
+            if (pnext <= P1) {
+                if (lane == 0) {
+                    const uint32_t q = pfetch % NP;
+                    mbar_expect_tx(s_pbar + q * 8, 256);
+                    bulk_g2s(s_idx + q * 256, a.cw + (size_t)pnext * 32, 256, s_pbar + q * 8, pol_cold);
+                }
+                ++pfetch;
+                ++pnext;
+            }
+        };
+        auto wait_piece = [&]() {                                        // the next piece in FIFO order has landed
+            pslot = pwait % NP;
+            mbar_wait(s_pbar + pslot * 8, (pwait / NP) & 1);
+            ++pwait;
+        };
+        // issue group `gi` (sub-group qs of the piece in ring slot `pslot`) into slot group sg
+        auto issue_group = [&](int gi, const int qs, const int sg) {
+            if (gi < gA || gi > gB) {
+                vmask[sg] = 0;
+                if (MODE == 1) cp_async_commit();
+                return;
+            }
+            int2 cw = make_int2(0, 0);
+            if (lane < G) cw = idx_gen[pslot * 32 + qs * 8 + lane];
+            bool valid = lane < G;
+            uint32_t vm = 0xffu;
+            if (gi == gA || gi == gB) {                                  // first / last group of the block: mask
+                const int e = gi * 8 + lane;
+                valid = valid && e >= e0 && e < e1;
+                vm = __ballot_sync(0xffffffffu, valid);
+            }
+            emask[sg] = __ballot_sync(0xffffffffu, valid && (cw.x & lastmask));
+            vmask[sg] = vm;
+            if (lane < G) w_slot[sg * G + lane] = valid ? __int_as_float(cw.y) : 0.f;
+            const unsigned cj = (unsigned)(cw.x & kColMask);
+            const char* src = (cj >= usplit ? hb1 : hb0) + (size_t)cj * pitch;
+            const unsigned long long pol = (cw.x & kColdFlag) ? pol_cold : pol_hot;
+            if (MODE == 0 || MODE == 2) {
+                if (lane == 0) mbar_expect_tx(s_gbar + sg * 8, (uint32_t)__popc(vm) * RB);
+                bool single = valid;                                     // this lane copies its own row (1-D bulk)
+                if (MODE == 2 && vm == 0xffu) {
+                    // lanes 0 and 1 look at the four columns of their quad (entries 4q .. 4q+3 of this group)
+                    const unsigned c0 = (unsigned)__shfl_sync(0xffffffffu, cw.x, (lane & 1) * 4 + 0);
+                    const unsigned c1 = (unsigned)__shfl_sync(0xffffffffu, cw.x, (lane & 1) * 4 + 1);
+                    const unsigned c2 = (unsigned)__shfl_sync(0xffffffffu, cw.x, (lane & 1) * 4 + 2);
+                    const unsigned c3 = (unsigned)__shfl_sync(0xffffffffu, cw.x, (lane & 1) * 4 + 3);
+                    const unsigned r0 = c0 & kColMask, r1 = c1 & kColMask, r2 = c2 & kColMask, r3 = c3 & kColMask;
+                    const bool allown = r0 < usplit && r1 < usplit && r2 < usplit && r3 < usplit;
+                    const bool allhalo = r0 >= usplit && r1 >= usplit && r2 >= usplit && r3 >= usplit;
+                    const bool quad_ok = allown || allhalo;
+                    const uint32_t okmask = __ballot_sync(0xffffffffu, quad_ok) & 3u;
+                    single = valid && !((okmask >> (lane >> 2)) & 1);
+                    __syncwarp();
+                    if (lane < 2 && quad_ok) {
+                        const unsigned sub = allhalo ? (unsigned)a.split : 0u;
+                        const bool cold = (c0 & c1 & c2 & c3 & kColdFlag) != 0;
+                        tma_gather4(s_data + (sg * G + lane * 4) * RB, allhalo ? tm1 : tm0, (int)(blockIdx.y * (RB / 4)),
+                                    (int)(r0 - sub), (int)(r1 - sub), (int)(r2 - sub), (int)(r3 - sub),
+                                    s_gbar + sg * 8, cold ? pol_cold : pol_hot);
+                    }
+                } else {
+                    __syncwarp();
+                }
+                if (single) bulk_g2s(s_data + (sg * G + lane) * RB, src, RB, s_gbar + sg * 8, pol);
+            } else {
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    const unsigned long long sj = __shfl_sync(0xffffffffu, (unsigned long long)src, j);
+                    const unsigned long long pj = __shfl_sync(0xffffffffu, pol, j);
+                    if (vm >> j & 1) {
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v)
+                            cp_async16(s_data + (sg * G + j) * RB + v * 512 + lane * 16,
+                                       reinterpret_cast<const char*>(sj) + v * 512 + lane * 16, pj);
+                    }
+                }
+                cp_async_commit();
+                __syncwarp();
+            }
+        };
+        auto flush_row = [&]() {
+            ring_store_row<VPL>(acc[0], acc[VPL - 1], a.rowids, row, a.Z0, a.Z1, a.zsplit, pitch, toff + lane * 16, a.beta);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ++row;
+        };
+        auto consume_group = [&](const int sg) {
+            const uint32_t vm = vmask[sg];
+            if (vm == 0) {                                               // group outside the block: nothing was issued
+                if (MODE == 1) cp_async_wait<NG - 1>();
+                return;
+            }
+            if (MODE != 1) { mbar_wait(s_gbar + sg * 8, (gpar >> sg) & 1); gpar ^= 1u << sg; }
+            else cp_async_wait<NG - 1>();
+            const uint32_t em = emask[sg];
+            const float4* slot = data_gen + (size_t)(sg * G) * (RB / 16);
+            if (vm == 0xffu) {
+                const float4 wa = *reinterpret_cast<const float4*>(w_slot + sg * G);
+                const float4 wb = *reinterpret_cast<const float4*>(w_slot + sg * G + 4);
+                const float w[G] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                float4 r[G][VPL];
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) r[j][v] = slot[j * (RB / 16) + v * 32];
+                if (em == 0) {                                           // no row ends inside: 8 x (LDS.128, 4 FFMA)
+#pragma unroll
+                    for (int j = 0; j < G; ++j)
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) vfma(acc[v], w[j], r[j][v]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < G; ++j) {
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) vfma(acc[v], w[j], r[j][v]);
+                        if (em >> j & 1) flush_row();
+                    }
+                }
+            } else {                                                     // first / last group of a block
+#pragma unroll 1
+                for (int j = 0; j < G; ++j) {
+                    if (vm >> j & 1) {
+                        const float wj = w_slot[sg * G + j];
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) vfma(acc[v], wj, slot[j * (RB / 16) + v * 32]);
+                        if (em >> j & 1) flush_row();
+                    }
+                }
+            }
+            __syncwarp();                                                // every lane is done with these slots
+        };
+
+        // prologue: index pieces in flight, first piece landed, first NG groups of it issued
+#pragma unroll
+        for (int i = 0; i < NP; ++i) fetch_piece();
+        wait_piece();
+#pragma unroll
+        for (int q = 0; q < NG; ++q) issue_group(4 * P0 + q, q, q);
+        if (NG == 4) fetch_piece();                                      // piece P0 fully issued: its slot is free
+
+        for (int P = P0; P <= P1; ++P) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int sg = q % NG;
+                consume_group(sg);
+                const int qi = (q + NG) % 4;                             // sub-group of the group NG ahead
+                const int Pi = P + (q + NG) / 4;                         // its piece
+                if (qi == 0 && Pi <= P1) wait_piece();                   // first group of a new piece
+                if (Pi <= P1) issue_group(4 * Pi + qi, qi, sg);
+                else { vmask[sg] = 0; if (MODE == 1) cp_async_commit(); }
+                if (qi == 3) fetch_piece();                              // that piece is fully issued now
+            }
+        }
+
+        if (seg) {
+            char* pb = reinterpret_cast<char*>(a.partial) + (size_t)(unsigned)(-b.y - 1) * pitch + toff;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                reinterpret_cast<float4*>(pb + v * 512)[lane] = acc[v];
+                acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+
+        if (!counter) break;
+        if (lane == 0) blk = (int)atomicAdd(counter, 1u);
+        blk = __shfl_sync(0xffffffffu, blk, 0);
+    }
+    if (MODE == 1) cp_async_wait<0>();
+}
+
+template <int VPL, int NS, int MODE>
+__global__ void __launch_bounds__(kRingWarps * 32)
+spmm_ring_kernel(const SpmmArgs a, const RingArgs ra)
+{
+    ring_body<VPL, NS, MODE>(a, ra, nullptr, nullptr);
+}
+
+// gather4 variant: the tensor maps of H_own (tm0) and of the halo slab (tm1) travel as __grid_constant__ parameters
+template <int VPL, int NS>
+__global__ void __launch_bounds__(kRingWarps * 32)
+spmm_ring_g4_kernel(const SpmmArgs a, const RingArgs ra, const __grid_constant__ CUtensorMap tm0,
+                    const __grid_constant__ CUtensorMap tm1)
+{
+    ring_body<VPL, NS, 2>(a, ra, &tm0, &tm1);
+}
+
+}  // namespace pgcn

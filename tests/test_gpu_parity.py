@@ -159,6 +159,7 @@ def test_schedule_options_do_not_change_results(opts):
     plans = make_plans(A, np.zeros(n, dtype=np.int64), 1, f)
     Z64 = orc.truth_forward(A, H)
     tol = fp32_tol(A, H, int(orc.row_degree(A).max()))
+    opts = dict(opts, kernel=4)                  # the register-pipeline kernel (the ring kernel has its own test)
     z1 = forward_all(plans, H, **opts)[0]
     z2 = forward_all(plans, H, **opts)[0]
     assert torch.equal(z1, z2)
@@ -166,6 +167,45 @@ def test_schedule_options_do_not_change_results(opts):
     if "long_row" in opts and opts["long_row"] <= 64:
         assert plans[0].get_option("long_rows_fwd") > 0
     plans[0].close()
+
+
+@pytest.mark.parametrize("f", [128, 256, 384, 512])
+@pytest.mark.parametrize("opts", [
+    dict(kernel=5), dict(kernel=6), dict(kernel=5, ring_slots=16, ring_edges_per_block=64),
+    dict(kernel=5, ring_slots=32, ring_edges_per_block=100, ring_long_row=150),
+    dict(kernel=5, persistent=1, ring_edges_per_block=256), dict(kernel=6, persistent=1, ring_slots=16, ring_edges_per_block=77),
+    dict(kernel=6, ring_slots=32, ring_edges_per_block=4096),
+    dict(kernel=7), dict(kernel=7, ring_slots=16, ring_edges_per_block=90, persistent=1),
+])
+def test_ring_kernel_matches_truth_and_register_kernel(f, opts):
+    """The shared-memory ring SpMM (TMA bulk copies / cp.async into per-warp row slots): every ring depth,
+    block size (blocks that start and end anywhere inside a 32-entry index piece, hub rows split into
+    segments), persistent CTAs with dynamic block fetch, 2-rank plans with a halo slab, forward and
+    transposed — same numbers as the fp64 truth within the fp32 bound, bit-identical run to run, and equal
+    to the register-pipeline kernel within fp32 reassociation."""
+    n = 4000
+    A = skewed_graph(n, 120000, seed=11)
+    rng = np.random.RandomState(f)
+    H = rng.uniform(-1, 1, size=(n, f)).astype(np.float32)
+    G = rng.uniform(-1, 1, size=(n, f)).astype(np.float32)
+    Z64 = orc.truth_forward(A, H); G64 = orc.truth_backward(A, G)
+    tolZ = fp32_tol(A, H, int(orc.row_degree(A).max())); tolG = fp32_tol(A.T, G, int(orc.row_degree(A.T).max()))
+    for k in (1, 2):
+        pv = np.zeros(n, dtype=np.int64) if k == 1 else graphio.random_partvec(n, 2, seed=5)
+        plans = make_plans(A, pv, k, f)
+        z1 = forward_all(plans, H, **opts)
+        z2 = forward_all(plans, H, **opts)
+        gd = backward_all(plans, G)
+        zr = forward_all(plans, H, kernel=4)
+        for r, p in enumerate(plans):
+            own = p.lp.owned
+            assert torch.equal(z1[r], z2[r])
+            assert_close_fp32(z1[r].cpu().numpy(), Z64[own], tolZ[own], "ring fwd %s f=%d k=%d r%d" % (opts, f, k, r))
+            assert_close_fp32(gd[r].cpu().numpy(), G64[own], tolG[own], "ring bwd %s f=%d k=%d r%d" % (opts, f, k, r))
+            torch.testing.assert_close(z1[r], zr[r], rtol=1e-4, atol=1e-5)
+            if k == 1 and opts.get("ring_edges_per_block", 1024) <= 100:
+                assert p.get_option("ring_long_rows_fwd") > 0
+            p.close()
 
 
 def test_empty_rank_and_tiny_graphs():

@@ -136,6 +136,15 @@ def main():
     elif args.sweep == "epb":
         for epb, lr in itertools.product((64, 96, 128, 160, 192, 256, 384), (0, 100000)):
             point({"edges_per_block": epb, "tile_floats": 0, "long_row": lr})
+    elif args.sweep == "ring":
+        # register pipeline (kernel 4) vs the shared-memory ring filled by TMA bulk copies (5) / cp.async (6)
+        point({"kernel": 4})
+        for kern, slots, epb, pers in itertools.product((5, 6, 7), (16, 32), (256, 512, 1024), (0, 1)):
+            point({"kernel": kern, "ring_slots": slots, "ring_edges_per_block": epb, "persistent": pers})
+    elif args.sweep == "ring-small":
+        point({"kernel": 4})
+        for kern, slots, epb, pers in ((5, 32, 1024, 0), (5, 16, 1024, 0), (5, 32, 2048, 1), (6, 32, 1024, 0), (6, 16, 1024, 0)):
+            point({"kernel": kern, "ring_slots": slots, "ring_edges_per_block": epb, "persistent": pers})
     elif args.sweep == "mini":
         for epb in (128, 160):
             point({"edges_per_block": epb, "tile_floats": 0})
