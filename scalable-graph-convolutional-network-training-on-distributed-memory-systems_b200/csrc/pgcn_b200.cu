@@ -10,6 +10,7 @@
 #include "spmm_ring.cuh"
 
 #include <dlfcn.h>
+#include <unistd.h>
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -81,6 +82,11 @@ struct DevCsr {
     int* d_rowids = nullptr;        // compact row -> output row, null when the identity
     int* d_empty = nullptr;         // output rows without entries (zero-filled when beta == 0)
     int nempty = 0;
+    bool view = false;              // a row range of another matrix: d_cw / d_rowids / d_empty are borrowed
+    int row_base = 0;               // compact id of the first walked row (views: offset into the parent's numbering)
+    std::vector<int> h_rowids, h_empty;   // host copies (parents of views only)
+    int64_t tuned_epb[2] = {0, 0};  // per-matrix autotune results (0: use the plan option): [0] register, [1] ring
+    int tuned_slots = 0;
     // schedules: [0] register-pipeline kernel (small row blocks, one per lane group),
     //            [1] shared-memory ring kernel (large row blocks, one per warp)
     struct Sched {
@@ -99,6 +105,8 @@ struct P2PBlob {                     // what pgcn_p2p_export writes (PGCN_P2P_HA
     int64_t arena_bytes;
     int64_t off_flags, off_fwd[2], off_bwd[2];
     int32_t k, rank, f_max, pad;
+    int64_t pid;                     // exporting process: a peer in the same process is reached through local_ptr
+    void* local_ptr;
     int64_t send_off[kMaxPeers + 1];
     int64_t recv_off[kMaxPeers + 1];
 };
@@ -110,7 +118,12 @@ struct pgcn_plan {
     int device = 0;
     int m = 0, h = 0, k = 1, rank = 0, f_max = 0;
     int64_t S = 0;
-    DevCsr fwd, tr, own, halo;       // halo: compact rows, see halo_rowmap
+    DevCsr fwd, tr;                  // A_local over [own | halo] columns, and its transpose
+    // split A_local = [A_own | A_halo(peer 0) | ... ] (Parallel-GCN/main.c:271 then :295 per received block):
+    DevCsr own;                      // columns < m
+    std::vector<DevCsr> halo_q;      // per source peer: boundary rows x that peer's columns (slab-relative)
+    DevCsr tr_own;                   // view: rows [0, m) of tr
+    std::vector<DevCsr> tr_halo_q;   // views: rows of tr that belong to each peer
     bool have_split = false;
     int64_t cols_ref = 0, rows_ref_t = 0;
 
@@ -128,11 +141,11 @@ struct pgcn_plan {
     // options
     int64_t opt_epb = 128, opt_long = 0, opt_tile = 0, opt_overlap = 1, opt_hot_mb = 64;
     // kernel: 0 auto (ring with TMA bulk copies where it applies), 4 register pipeline, 5 ring/1-D TMA,
-    //         6 ring/cp.async, 7 ring/TMA tile::gather4
-    int64_t opt_g4_box = 1;
-    int64_t opt_kernel = 0, opt_ring_slots = 32, opt_ring_epb = 1024, opt_ring_long = 0, opt_persistent = 0;
-    bool ring_attr_set[12] = {false};
-    int ring_ctas_per_sm[12] = {0};
+    //         6 ring/cp.async, 7 ring/TMA tile::gather4 (= auto)
+    int64_t opt_ring_groups = 2;
+    int64_t opt_kernel = 0, opt_ring_slots = 16, opt_ring_epb = 512, opt_ring_long = 0, opt_persistent = 1;
+    bool ring_attr_set[48] = {false};
+    int ring_ctas_per_sm[48] = {0};
     unsigned int* d_counter = nullptr;     // block counters of the persistent ring kernel (one per feature tile)
     int num_sms = 148;
 
@@ -141,12 +154,16 @@ struct pgcn_plan {
     cudaStream_t comm_stream = nullptr;
     cudaStream_t host_stream = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    std::vector<cudaEvent_t> ev_step;      // one per peer step of the pipelined exchange
+    unsigned int* d_done = nullptr;        // per-destination CTA counters of put_rows_kernel
 
     // peer-memory transport
     bool p2p = false;
+    int64_t opt_p2p = 1;                   // 0: never use the peer transport (all ranks must agree)
     void* arena = nullptr; int64_t arena_bytes = 0;
     int64_t off_flags = 0, off_fwd[2] = {0, 0}, off_bwd[2] = {0, 0};
     void* peer_arena[kMaxPeers] = {nullptr};
+    bool peer_local[kMaxPeers] = {false};   // peer lives in THIS process (same-process plans: no IPC mapping)
     P2PBlob peer_blob[kMaxPeers];
     unsigned long long epoch = 0;
 
@@ -201,7 +218,8 @@ int upload(pgcn_plan* p, T** dst, const T* src, size_t n)
 // below which a column is COLD (-1: no marking): cold columns get kColdFlag and are gathered with an
 // L2 evict_first policy, the most-referenced rows of H (as many as fit the hot budget) evict_last.
 int csr_upload(pgcn_plan* p, DevCsr& c, int nrows, const int* rowptr, const int* colidx, const float* vals,
-               const std::vector<int>* ext_rowmap = nullptr, const int* col_refs = nullptr, int cold_thresh = -1)
+               const std::vector<int>* ext_rowmap = nullptr, const int* col_refs = nullptr, int cold_thresh = -1,
+               bool keep_host = false)
 {
     c.nrows = nrows;
     c.nnz = rowptr[nrows];
@@ -236,12 +254,37 @@ int csr_upload(pgcn_plan* p, DevCsr& c, int nrows, const int* rowptr, const int*
     if (c.nempty > 0) {
         if ((rc = upload(p, &c.d_empty, empty.data(), empty.size()))) return rc;
     }
+    if (keep_host) { c.h_rowids.swap(rowids); c.h_empty.swap(empty); }
     return 0;
+}
+
+// Rows [r0, r1) of an uploaded matrix as a matrix of its own (no copy): the transposed CSR's own rows and the
+// rows that belong to one peer are contiguous row ranges, so the pipelined backward needs no second copy of A^T.
+void csr_view(const DevCsr& base, DevCsr& v, int r0, int r1)
+{
+    v = DevCsr();
+    v.view = true;
+    int c0 = r0, c1 = r1, e0 = 0, e1 = 0;
+    if (base.d_rowids) {                     // rows were squeezed: compact ids of the range
+        c0 = (int)(std::lower_bound(base.h_rowids.begin(), base.h_rowids.end(), r0) - base.h_rowids.begin());
+        c1 = (int)(std::lower_bound(base.h_rowids.begin(), base.h_rowids.end(), r1) - base.h_rowids.begin());
+        e0 = (int)(std::lower_bound(base.h_empty.begin(), base.h_empty.end(), r0) - base.h_empty.begin());
+        e1 = (int)(std::lower_bound(base.h_empty.begin(), base.h_empty.end(), r1) - base.h_empty.begin());
+    }
+    v.nrows = r1 - r0;
+    v.nrows_c = c1 - c0;
+    v.row_base = c0;
+    v.h_rowptr.assign(base.h_rowptr.begin() + c0, base.h_rowptr.begin() + c1 + 1);   // absolute entry offsets
+    v.nnz = (int64_t)v.h_rowptr.back() - v.h_rowptr.front();
+    v.d_cw = base.d_cw;
+    v.d_rowids = base.d_rowids;
+    v.d_empty = base.d_empty ? base.d_empty + e0 : nullptr;
+    v.nempty = e1 - e0;
 }
 
 void csr_free(DevCsr& c)
 {
-    cudaFree(c.d_cw); cudaFree(c.d_rowids); cudaFree(c.d_empty);
+    if (!c.view) { cudaFree(c.d_cw); cudaFree(c.d_rowids); cudaFree(c.d_empty); }
     for (auto& sc : c.sched) { cudaFree(sc.d_blocks); cudaFree(sc.d_long); cudaFree(sc.d_partial); }
     c = DevCsr();
 }
@@ -253,7 +296,7 @@ constexpr int kMaxRowsPerBlock = 128;
 // Pure host function (also reachable through pgcn_debug_schedule for CPU-side tests).
 void make_schedule(const int* rp, int nrows_c, int64_t epb, int64_t long_row,
                    std::vector<int4>& blocks, std::vector<int4>& longs, int& nslots,
-                   int max_rows = kMaxRowsPerBlock)
+                   int max_rows = kMaxRowsPerBlock, int row_base = 0)
 {
     blocks.clear(); longs.clear(); nslots = 0;
     const int64_t nnz = nrows_c > 0 ? rp[nrows_c] : 0;
@@ -262,7 +305,7 @@ void make_schedule(const int* rp, int nrows_c, int64_t epb, int64_t long_row,
     int64_t cur_edges = 0;
     auto close = [&](int row_end) {
         if (row_end > cur_begin)
-            blocks.push_back(make_int4(cur_begin, row_end - cur_begin, rp[cur_begin], rp[row_end]));
+            blocks.push_back(make_int4(row_base + cur_begin, row_end - cur_begin, rp[cur_begin], rp[row_end]));
         cur_begin = row_end;
         cur_edges = 0;
     };
@@ -271,11 +314,11 @@ void make_schedule(const int* rp, int nrows_c, int64_t epb, int64_t long_row,
         if (d > long_row) {
             close(r);
             const int nseg = (int)((d + epb - 1) / epb);
-            longs.push_back(make_int4(r, nslots, nseg, 0));
+            longs.push_back(make_int4(row_base + r, nslots, nseg, 0));
             for (int s = 0; s < nseg; ++s) {
                 const int e0 = rp[r] + (int)(s * epb);
                 const int e1 = (int)std::min<int64_t>((int64_t)rp[r + 1], (int64_t)e0 + epb);
-                blocks.push_back(make_int4(r, -(nslots + 1), e0, e1));
+                blocks.push_back(make_int4(row_base + r, -(nslots + 1), e0, e1));
                 ++nslots;
             }
             cur_begin = r + 1;
@@ -296,7 +339,7 @@ int build_schedule(pgcn_plan* p, DevCsr& c, int which, int64_t epb, int64_t long
     std::vector<int4> blocks, longs;
     int nslots = 0;
     make_schedule(c.h_rowptr.data(), c.nrows_c, epb, long_row, blocks, longs, nslots,
-                  which == 1 ? (1 << 30) : kMaxRowsPerBlock);
+                  which == 1 ? (1 << 30) : kMaxRowsPerBlock, c.row_base);
 
     cudaFree(sc.d_blocks); cudaFree(sc.d_long); cudaFree(sc.d_partial);
     sc.d_blocks = nullptr; sc.d_long = nullptr; sc.d_partial = nullptr;
@@ -395,16 +438,35 @@ bool make_row_map(CUtensorMap* tm, const float* base, int64_t rows, int f, int t
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int VPL, int MODE>
-ring_fn pick_ring_ns(int ns)
-{
-    return ns == 16 ? spmm_ring_kernel<VPL, 16, MODE> : spmm_ring_kernel<VPL, 32, MODE>;
-}
+// Ring kernel instances: shape id = 0: G=8,NG=2 (16 slots)  1: G=16,NG=2 (32)  2: G=32,NG=2 (64)  3: G=16,NG=4 (64)
+struct RingShape { int g, ng; };
+const RingShape kRingShapes[4] = {{8, 2}, {16, 2}, {32, 2}, {16, 4}};
 
-ring_fn pick_ring(int vpl, int ns, int mode)
+template <int VPL, bool HALO>
+ring_fn pick_ring_t(int shape, int mode)
 {
-    if (vpl == 2) return mode ? pick_ring_ns<2, 1>(ns) : pick_ring_ns<2, 0>(ns);
-    return mode ? pick_ring_ns<1, 1>(ns) : pick_ring_ns<1, 0>(ns);
+    if (mode == 1) return spmm_ring_kernel<VPL, 8, 2, 1, HALO>;
+    return shape == 1 ? spmm_ring_kernel<VPL, 16, 2, 0, HALO> : spmm_ring_kernel<VPL, 8, 2, 0, HALO>;
+}
+ring_fn pick_ring(int vpl, int shape, int mode, bool halo)
+{
+    if (vpl == 2) return halo ? pick_ring_t<2, true>(shape, mode) : pick_ring_t<2, false>(shape, mode);
+    return halo ? pick_ring_t<1, true>(shape, mode) : pick_ring_t<1, false>(shape, mode);
+}
+template <int VPL, bool HALO>
+ring_g4_fn pick_ring_g4_t(int shape)
+{
+    switch (shape) {
+        case 1: return spmm_ring_g4_kernel<VPL, 16, 2, HALO>;
+        case 2: return spmm_ring_g4_kernel<VPL, 32, 2, HALO>;
+        case 3: return spmm_ring_g4_kernel<VPL, 16, 4, HALO>;
+        default: return spmm_ring_g4_kernel<VPL, 8, 2, HALO>;
+    }
+}
+ring_g4_fn pick_ring_g4(int vpl, int shape, bool halo)
+{
+    if (vpl == 2) return halo ? pick_ring_g4_t<2, true>(shape) : pick_ring_g4_t<2, false>(shape);
+    return halo ? pick_ring_g4_t<1, true>(shape) : pick_ring_g4_t<1, false>(shape);
 }
 
 bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
@@ -424,10 +486,10 @@ int launch_spmm(pgcn_plan* p, DevCsr& c, const float* H0, const float* H1, int s
     const bool ring = use_ring(p, H0, H1, f) && aligned16(Z0) && aligned16(Z1);
     int64_t epb, long_row;
     if (ring) {
-        epb = std::max<int64_t>(p->opt_ring_epb, 64);
+        epb = std::max<int64_t>(c.tuned_epb[1] > 0 ? c.tuned_epb[1] : p->opt_ring_epb, 64);
         long_row = p->opt_ring_long > 0 ? p->opt_ring_long : 2 * epb;
     } else {
-        epb = std::max<int64_t>(p->opt_epb, 8);
+        epb = std::max<int64_t>(c.tuned_epb[0] > 0 ? c.tuned_epb[0] : p->opt_epb, 8);
         long_row = p->opt_long > 0 ? p->opt_long : 4 * epb;
     }
     int rc = build_schedule(p, c, ring ? 1 : 0, epb, long_row);
@@ -453,28 +515,29 @@ int launch_spmm(pgcn_plan* p, DevCsr& c, const float* H0, const float* H1, int s
     if (sc.nblocks > 0 && ring) {
         const int vpl = (f % 256 == 0) ? 2 : 1;
         const int tiles = f / (128 * vpl);
-        int ns = (int)p->opt_ring_slots;
-        if (ns != 16) ns = 32;
-        int mode = p->opt_kernel == 6 ? 1 : (p->opt_kernel == 7 ? 2 : 0);
+        const bool halo = (H1 != nullptr);
+        int mode = p->opt_kernel == 6 ? 1 : (p->opt_kernel == 5 ? 0 : 2);   // default: tile::gather4
+        // ring shape from the options: ring_slots = 16 | 32 | 64, ring_groups = 2 | 4 (only with 64 slots)
+        const int64_t want_slots = c.tuned_slots > 0 ? c.tuned_slots : p->opt_ring_slots;
+        int shape = want_slots <= 16 ? 0 : (want_slots <= 32 ? 1 : (p->opt_ring_groups == 4 ? 3 : 2));
         CUtensorMap tm0, tm1;
         if (mode == 2) {
             // H0 holds the columns below `split` (all of them when there is no halo slab), H1 the rest
             const int tile = 128 * vpl;
-            const int box_rows = (int)p->opt_g4_box;
-            bool ok = make_row_map(&tm0, H0, 1 << 30, f, tile, box_rows);
-            if (ok && H1) ok = make_row_map(&tm1, H1, 1 << 30, f, tile, box_rows);
+            bool ok = make_row_map(&tm0, H0, 1 << 30, f, tile, 1);
+            if (ok && H1) ok = make_row_map(&tm1, H1, 1 << 30, f, tile, 1);
             else if (ok) tm1 = tm0;
             if (!ok) mode = 0;                                   // no driver entry point: 1-D bulk copies
         }
-        ring_fn fn = mode == 2 ? nullptr : pick_ring(vpl, ns, mode);
-        ring_g4_fn fn4 = nullptr;
-        if (mode == 2)
-            fn4 = vpl == 2 ? (ns == 16 ? spmm_ring_g4_kernel<2, 16> : spmm_ring_g4_kernel<2, 32>)
-                           : (ns == 16 ? spmm_ring_g4_kernel<1, 16> : spmm_ring_g4_kernel<1, 32>);
+        if (mode == 1) shape = 0;
+        if (mode == 0 && shape > 1) shape = 1;
+        const int g = kRingShapes[shape].g, ng = kRingShapes[shape].ng;
+        ring_fn fn = mode == 2 ? nullptr : pick_ring(vpl, shape, mode, halo);
+        ring_g4_fn fn4 = mode == 2 ? pick_ring_g4(vpl, shape, halo) : nullptr;
         const void* fptr = mode == 2 ? (const void*)fn4 : (const void*)fn;
-        const size_t smem = ring_smem_bytes(vpl, ns);
+        const size_t smem = ring_smem_bytes(vpl, g * ng, ng);
         // opt-in to > 48 KB of dynamic shared memory, once per kernel instance
-        const int slot = ((vpl - 1) * 2 + (ns == 16 ? 0 : 1)) * 3 + mode;
+        const int slot = (((vpl - 1) * 4 + shape) * 3 + mode) * 2 + (halo ? 1 : 0);
         if (!p->ring_attr_set[slot]) {
             CU(p, cudaFuncSetAttribute(fptr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int nb = 0;
@@ -528,16 +591,11 @@ unsigned grid_for(long long total)
     return (unsigned)std::max<long long>(1, std::min<long long>(g, 148LL * 32));
 }
 
-int launch_pack(pgcn_plan* p, const float* H, float* slab, float* const* peer_dst, int f, cudaStream_t st)
+int launch_pack(pgcn_plan* p, const float* H, float* slab, int f, cudaStream_t st)
 {
     if (p->S == 0) return 0;
     PackArgs a;
-    a.send_idx = p->d_send_idx; a.S = p->S; a.H = H; a.slab = slab; a.k = p->k; a.f = f;
-    a.to_peers = peer_dst != nullptr;
-    if (a.to_peers) {                                     // peer transport: k <= kMaxPeersDev (pgcn_p2p_export)
-        for (int i = 0; i <= p->k; ++i) a.send_off[i] = p->send_off[i];
-        for (int i = 0; i < p->k; ++i) a.peer_dst[i] = peer_dst[i];
-    }
+    a.send_idx = p->d_send_idx; a.S = p->S; a.H = H; a.slab = slab; a.f = f;
     const int vw = (f % 4 == 0) ? 4 : 1;
     const unsigned grid = grid_for(p->S * (f / vw));
     if (vw == 4) pack_rows_kernel<4><<<grid, 256, 0, st>>>(a);
@@ -584,21 +642,41 @@ int nccl_exchange(pgcn_plan* p, const float* send, float* recv, int f, int rever
 
 float* arena_ptr(void* base, int64_t off) { return reinterpret_cast<float*>(static_cast<char*>(base) + off); }
 
-int p2p_signal_wait(pgcn_plan* p, cudaStream_t st, bool do_signal, bool do_wait)
+unsigned long long* flag_slot(void* arena, int64_t off_flags, int slot)
 {
-    if (do_signal) {
-        FlagPtrs fp;
-        for (int q = 0; q < p->k; ++q)
-            fp.p[q] = reinterpret_cast<unsigned long long*>(static_cast<char*>(p->peer_arena[q]) + p->peer_blob[q].off_flags);
-        p2p_signal_kernel<<<1, 32, 0, st>>>(fp, p->k, p->rank, p->epoch);
-        ++p->launches;
+    return reinterpret_cast<unsigned long long*>(static_cast<char*>(arena) + off_flags) + slot;
+}
+
+// Fused put of the rows bound for peer `dst` + epoch signal (peer-memory transport). `reverse`: halo partials of
+// A^T g back to their owner (rows already in wire order), else boundary rows of H gathered through send_idx.
+int p2p_put(pgcn_plan* p, int dst, const float* src, int f, bool reverse, int par, cudaStream_t st)
+{
+    PutArgs a;
+    const P2PBlob& pb = p->peer_blob[dst];
+    if (!reverse) {
+        a.send_idx = p->d_send_idx; a.j0 = p->send_off[dst]; a.nrows = p->send_off[dst + 1] - p->send_off[dst];
+        a.dst = arena_ptr(p->peer_arena[dst], pb.off_fwd[par]) + (size_t)pb.recv_off[p->rank] * f;
+    } else {
+        a.send_idx = nullptr; a.j0 = p->recv_off[dst]; a.nrows = p->recv_off[dst + 1] - p->recv_off[dst];
+        a.dst = arena_ptr(p->peer_arena[dst], pb.off_bwd[par]) + (size_t)pb.send_off[p->rank] * f;
     }
-    if (do_wait) {
-        const unsigned long long* mine =
-            reinterpret_cast<const unsigned long long*>(static_cast<char*>(p->arena) + p->off_flags);
-        p2p_wait_kernel<<<1, 32, 0, st>>>(mine, p->k, p->rank, p->epoch);
-        ++p->launches;
-    }
+    a.src = src; a.f = f;
+    a.done = p->d_done + (reverse ? 32 : 0) + dst;     // kMaxPeers <= 16 destinations per direction
+    a.flag = flag_slot(p->peer_arena[dst], pb.off_flags, p->rank);
+    a.epoch = p->epoch;
+    // enough CTAs to keep the NVLink store queues full, few enough not to crowd out the SpMM running beside it
+    const long long items = a.nrows * (f / 4);
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((items + 255) / 256, 4LL * p->num_sms));
+    put_rows_kernel<4><<<grid, 256, 0, st>>>(a);
+    ++p->launches;
+    CU(p, cudaGetLastError());
+    return 0;
+}
+
+int p2p_wait(pgcn_plan* p, int src, cudaStream_t st)
+{
+    p2p_wait_kernel<<<1, 32, 0, st>>>(flag_slot(p->arena, p->off_flags, src), p->epoch);
+    ++p->launches;
     CU(p, cudaGetLastError());
     return 0;
 }
@@ -674,29 +752,49 @@ int pgcn_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* 
     };
     const int cold_fwd = cold_threshold(refs_fwd), cold_tr = cold_threshold(refs_tr);
     TRY(csr_upload(p, p->fwd, m, rowptr, colidx, vals, nullptr, refs_fwd.data(), cold_fwd));
-    TRY(csr_upload(p, p->tr, m + h, t_rowptr, t_colidx, t_vals, nullptr, refs_tr.data(), cold_tr));
+    TRY(csr_upload(p, p->tr, m + h, t_rowptr, t_colidx, t_vals, nullptr, refs_tr.data(), cold_tr, true));
 
     // distinct referenced columns / transposed rows (for the roofline's compulsory bytes)
     for (int r = 0; r < m + h; ++r) if (t_rowptr[r + 1] > t_rowptr[r]) ++p->cols_ref;
     p->rows_ref_t = 0;
     for (int r = 0; r < m; ++r) if (rowptr[r + 1] > rowptr[r]) ++p->rows_ref_t;
 
-    // split A_local = [A_own | A_halo] (Parallel-GCN/main.c:271 then :295) for exchange/compute overlap
+    // split A_local = [A_own | A_halo(peer) ...] (Parallel-GCN/main.c:271 then :295 per received block) so that
+    // A_own * H_own overlaps the exchange and each peer's block is accumulated as soon as it has landed
     if (h > 0 && k > 1) {
         std::vector<int> o_rp(m + 1, 0), o_ci; std::vector<float> o_v;
-        std::vector<int> h_rp(1, 0), h_ci, h_map; std::vector<float> h_v;
         o_ci.reserve(nnz); o_v.reserve(nnz);
+        std::vector<std::vector<int>> q_rp((size_t)k, std::vector<int>(1, 0)), q_ci((size_t)k), q_map((size_t)k);
+        std::vector<std::vector<float>> q_v((size_t)k);
+        std::vector<int> col_peer((size_t)h);
+        for (int q = 0; q < k; ++q)
+            for (int64_t c = recv_off[q]; c < recv_off[q + 1]; ++c) col_peer[(size_t)c] = q;
+        std::vector<char> touched((size_t)k, 0);
         for (int r = 0; r < m; ++r) {
-            const size_t before = h_ci.size();
             for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
                 if (colidx[e] < m) { o_ci.push_back(colidx[e]); o_v.push_back(vals[e]); }
-                else { h_ci.push_back(colidx[e] - m); h_v.push_back(vals[e]); }   // slab-relative column
+                else {
+                    const int q = col_peer[(size_t)(colidx[e] - m)];
+                    q_ci[q].push_back(colidx[e] - m);                    // slab-relative column
+                    q_v[q].push_back(vals[e]);
+                    touched[q] = 1;
+                }
             }
             o_rp[r + 1] = (int)o_ci.size();
-            if (h_ci.size() > before) { h_map.push_back(r); h_rp.push_back((int)h_ci.size()); }
+            for (int q = 0; q < k; ++q)
+                if (touched[q]) { q_map[q].push_back(r); q_rp[q].push_back((int)q_ci[q].size()); touched[q] = 0; }
         }
         TRY(csr_upload(p, p->own, m, o_rp.data(), o_ci.data(), o_v.data(), nullptr, refs_fwd.data(), cold_fwd));
-        TRY(csr_upload(p, p->halo, (int)h_map.size(), h_rp.data(), h_ci.data(), h_v.data(), &h_map, refs_fwd.data() + m, cold_fwd));
+        p->halo_q.resize((size_t)k);
+        for (int q = 0; q < k; ++q) {
+            if (q_map[q].empty()) continue;
+            TRY(csr_upload(p, p->halo_q[q], (int)q_map[q].size(), q_rp[q].data(), q_ci[q].data(), q_v[q].data(), &q_map[q],
+                           refs_fwd.data() + m, cold_fwd));
+        }
+        csr_view(p->tr, p->tr_own, 0, m);
+        p->tr_halo_q.resize((size_t)k);
+        for (int q = 0; q < k; ++q)
+            if (recv_off[q + 1] > recv_off[q]) csr_view(p->tr, p->tr_halo_q[q], m + (int)recv_off[q], m + (int)recv_off[q + 1]);
         p->have_split = true;
     }
 
@@ -705,6 +803,7 @@ int pgcn_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* 
         if (cudaGetDeviceProperties(&prop, p->device) == cudaSuccess) p->num_sms = prop.multiProcessorCount;
         std::vector<unsigned int> zeros(64, 0u);
         TRY(upload(p, &p->d_counter, zeros.data(), zeros.size()));
+        TRY(upload(p, &p->d_done, zeros.data(), zeros.size()));
     }
     TRY(upload(p, &p->d_send_idx, send_idx, (size_t)S));
     // boundary CSR: for every owned row that appears in some send list, the slab positions
@@ -732,10 +831,16 @@ int pgcn_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* 
     TRY(slab(&p->d_rrecv_slab, S));
     TRY(slab(&p->d_hsend_slab, h));
     {
-        cudaError_t e1 = cudaStreamCreateWithFlags(&p->comm_stream, cudaStreamNonBlocking);
+        // the exchange stream outranks the compute stream: its (small) kernels must get SM slots while an SpMM
+        // grid is draining, because a neighbour is waiting for their stores
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        cudaError_t e1 = cudaStreamCreateWithPriority(&p->comm_stream, cudaStreamNonBlocking, prio_hi);
         if (e1 == cudaSuccess) e1 = cudaStreamCreateWithFlags(&p->host_stream, cudaStreamNonBlocking);
         cudaError_t e2 = cudaEventCreateWithFlags(&p->ev_a, cudaEventDisableTiming);
         cudaError_t e3 = cudaEventCreateWithFlags(&p->ev_b, cudaEventDisableTiming);
+        p->ev_step.assign((size_t)k, nullptr);
+        for (int q = 0; q < k && e3 == cudaSuccess; ++q) e3 = cudaEventCreateWithFlags(&p->ev_step[(size_t)q], cudaEventDisableTiming);
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
             fail(p, PGCN_ERR_CUDA, "stream/event creation failed");
             g_lib_error = p->err; pgcn_plan_destroy(p); return PGCN_ERR_CUDA;
@@ -753,9 +858,14 @@ int pgcn_plan_destroy(pgcn_plan* p)
     cudaDeviceSynchronize();
     if (p->comm && g_nccl.ok) g_nccl.CommDestroy(p->comm);
     for (int q = 0; q < kMaxPeers; ++q)
-        if (p->peer_arena[q] && q != p->rank) cudaIpcCloseMemHandle(p->peer_arena[q]);
+        if (p->peer_arena[q] && q != p->rank && !p->peer_local[q]) cudaIpcCloseMemHandle(p->peer_arena[q]);
     cudaFree(p->arena);
-    csr_free(p->fwd); csr_free(p->tr); csr_free(p->own); csr_free(p->halo);
+    csr_free(p->tr_own);
+    for (auto& c : p->tr_halo_q) csr_free(c);
+    for (auto& c : p->halo_q) csr_free(c);
+    csr_free(p->fwd); csr_free(p->tr); csr_free(p->own);
+    for (cudaEvent_t e : p->ev_step) if (e) cudaEventDestroy(e);
+    cudaFree(p->d_done);
     cudaFree(p->d_send_idx);
     cudaFree(p->d_brow); cudaFree(p->d_bptr); cudaFree(p->d_bpos);
     cudaFree(p->d_send_slab); cudaFree(p->d_halo_slab); cudaFree(p->d_rrecv_slab); cudaFree(p->d_hsend_slab);
@@ -779,11 +889,17 @@ int pgcn_plan_set_option(pgcn_plan* p, const char* name, int64_t value)
     else if (n == "ring_edges_per_block") p->opt_ring_epb = value;
     else if (n == "ring_long_row") p->opt_ring_long = value;
     else if (n == "persistent") p->opt_persistent = value;
-    else if (n == "g4_box_rows") p->opt_g4_box = value;
+    else if (n == "ring_groups") p->opt_ring_groups = value;
     else if (n == "long_row") p->opt_long = value;
     else if (n == "tile_floats") p->opt_tile = value;
     else if (n == "hot_mb") p->opt_hot_mb = value;
     else if (n == "overlap") p->opt_overlap = value;
+    else if (n == "p2p") {
+        // 0 = never use the peer transport even though pgcn_p2p_import succeeded here (another rank could not map
+        // its peers: every rank must then fall back to NCCL together); 1 re-enables it when the arenas are mapped.
+        p->opt_p2p = value ? 1 : 0;
+        p->p2p = p->opt_p2p && p->arena && p->peer_arena[p->rank];
+    }
     else return fail(p, PGCN_ERR_INVALID, "unknown option '%s'", name);
     return 0;
 }
@@ -798,6 +914,7 @@ int64_t pgcn_plan_get_option(const pgcn_plan* p, const char* name)
     if (n == "ring_edges_per_block") return p->opt_ring_epb;
     if (n == "ring_long_row") return p->opt_ring_long;
     if (n == "persistent") return p->opt_persistent;
+    if (n == "ring_groups") return p->opt_ring_groups;
     if (n == "long_row") return p->opt_long;
     if (n == "tile_floats") return p->opt_tile;
     if (n == "hot_mb") return p->opt_hot_mb;
@@ -948,6 +1065,7 @@ int pgcn_p2p_export(pgcn_plan* p, void* handle_out)
     b.arena_bytes = p->arena_bytes; b.off_flags = p->off_flags;
     for (int i = 0; i < 2; ++i) { b.off_fwd[i] = p->off_fwd[i]; b.off_bwd[i] = p->off_bwd[i]; }
     b.k = p->k; b.rank = p->rank; b.f_max = p->f_max;
+    b.pid = (int64_t)getpid(); b.local_ptr = p->arena;
     for (int i = 0; i <= p->k; ++i) { b.send_off[i] = p->send_off[i]; b.recv_off[i] = p->recv_off[i]; }
     memset(handle_out, 0, PGCN_P2P_HANDLE_BYTES);
     memcpy(handle_out, &b, sizeof b);
@@ -968,9 +1086,15 @@ int pgcn_p2p_import(pgcn_plan* p, const void* handles_k)
         if (b.recv_off[p->rank + 1] - b.recv_off[p->rank] != p->send_off[q + 1] - p->send_off[q])
             return fail(p, PGCN_ERR_INVALID, "send/recv count mismatch with peer %d", q);
         if (q == p->rank) { p->peer_arena[q] = p->arena; continue; }
+        if (p->peer_arena[q]) continue;                     // already mapped (import called twice)
+        if (b.pid == (int64_t)getpid()) {                   // a plan of this very process: plain device pointer
+            p->peer_arena[q] = b.local_ptr;
+            p->peer_local[q] = true;
+            continue;
+        }
         CU(p, cudaIpcOpenMemHandle(&p->peer_arena[q], b.ipc, cudaIpcMemLazyEnablePeerAccess));
     }
-    p->p2p = true;
+    p->p2p = p->opt_p2p != 0;
     return 0;
 }
 
@@ -991,7 +1115,12 @@ int pgcn_spmm(pgcn_plan* p, int transpose, const float* H_own, const float* H_ha
             return launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, f, 0, st);
         }
         if (!H_halo) return fail(p, PGCN_ERR_INVALID, "null H_halo");
-        return launch_spmm(p, p->halo, H_halo, nullptr, p->h, Z, nullptr, p->m, f, 1, st);
+        for (int q = 0; q < p->k; ++q) {                  // Z += A_halo(q) * H_halo, one source peer after the other
+            if (p->halo_q[(size_t)q].nrows == 0) continue;
+            int rc2 = launch_spmm(p, p->halo_q[(size_t)q], H_halo, nullptr, p->h, Z, nullptr, p->m, f, 1, st);
+            if (rc2) return rc2;
+        }
+        return 0;
     }
     if (!transpose) {
         if (p->m > 0 && (!H_own || !Z)) return fail(p, PGCN_ERR_INVALID, "null H_own/Z");
@@ -1008,7 +1137,7 @@ int pgcn_pack(pgcn_plan* p, const float* H, float* send_slab, int32_t f, void* s
     int rc = check_f(p, f);
     if (rc) return rc;
     if (p->S > 0 && (!H || !send_slab)) return fail(p, PGCN_ERR_INVALID, "null H/send_slab");
-    return launch_pack(p, H, send_slab, nullptr, f, (cudaStream_t)stream);
+    return launch_pack(p, H, send_slab, f, (cudaStream_t)stream);
 }
 
 int pgcn_exchange(pgcn_plan* p, const float* send_slab, float* recv_slab, int32_t f, int reverse, void* stream)
@@ -1026,6 +1155,26 @@ int pgcn_unpack_add(pgcn_plan* p, const float* recv_slab, float* G_own, int32_t 
     return launch_unpack(p, recv_slab, G_own, f, (cudaStream_t)stream);
 }
 
+// Exchange schedule shared by both transports and both directions: at step i = 1 .. k-1 a rank sends to
+// (rank + i) % k and receives from (rank - i) % k — every pair is active exactly once per step, and a receiver
+// sees its sources arrive one after the other, so each block can be consumed while the next is in flight.
+static inline int step_dst(const pgcn_plan* p, int i) { return (p->rank + i) % p->k; }
+static inline int step_src(const pgcn_plan* p, int i) { return (p->rank - i + p->k) % p->k; }
+
+static int nccl_step(pgcn_plan* p, const float* send, float* recv, int f, int reverse, int i, cudaStream_t st)
+{
+    const std::vector<int64_t>& so = reverse ? p->recv_off : p->send_off;
+    const std::vector<int64_t>& ro = reverse ? p->send_off : p->recv_off;
+    const int d = step_dst(p, i), s = step_src(p, i);
+    const int64_t ns = so[d + 1] - so[d], nr = ro[s + 1] - ro[s];
+    if (ns == 0 && nr == 0) return 0;
+    NC(p, g_nccl.GroupStart());
+    if (ns > 0) NC(p, g_nccl.Send(send + (size_t)so[d] * f, (size_t)ns * f, ncclFloat_, d, p->comm, st));
+    if (nr > 0) NC(p, g_nccl.Recv(recv + (size_t)ro[s] * f, (size_t)nr * f, ncclFloat_, s, p->comm, st));
+    NC(p, g_nccl.GroupEnd());
+    return 0;
+}
+
 int pgcn_forward(pgcn_plan* p, const float* H_own, float* Z, int32_t f, void* stream)
 {
     int rc = check_f(p, f);
@@ -1035,47 +1184,52 @@ int pgcn_forward(pgcn_plan* p, const float* H_own, float* Z, int32_t f, void* st
     if (p->k == 1)
         return launch_spmm(p, p->fwd, H_own, p->h > 0 ? p->d_halo_slab : nullptr, p->m, Z, nullptr, p->m, f, 0, st);
 
+    const bool use_p2p = p->p2p && (f % 4 == 0);
+    if (!use_p2p && !p->comm) return fail(p, PGCN_ERR_STATE, "k=%d: call pgcn_comm_init or pgcn_p2p_import first", p->k);
     const bool split = p->have_split && p->opt_overlap;
-    if (p->p2p && (f % 4 == 0)) {
-        // peer-memory transport: rows go straight into the neighbours' halo slabs
+    const int k = p->k;
+    float* halo = p->d_halo_slab;
+    int par = 0;
+    if (use_p2p) {
         ++p->epoch;
-        const int par = (int)(p->epoch & 1);
-        float* dst[kMaxPeers];
-        for (int q = 0; q < p->k; ++q)
-            dst[q] = arena_ptr(p->peer_arena[q], p->peer_blob[q].off_fwd[par]) + (size_t)p->peer_blob[q].recv_off[p->rank] * f;
-        float* halo = arena_ptr(p->arena, p->off_fwd[par]);
-        if (split) {
-            // side stream: rows leave for the neighbours' slabs (NVLink-bound) ; main stream: own-columns SpMM.
-            // The neighbours' rows land in MY slab meanwhile; the wait kernel joins on their epoch flags.
-            CU(p, cudaEventRecord(p->ev_a, st));
-            CU(p, cudaStreamWaitEvent(p->comm_stream, p->ev_a, 0));
-            if ((rc = launch_pack(p, H_own, nullptr, dst, f, p->comm_stream))) return rc;
-            if ((rc = p2p_signal_wait(p, p->comm_stream, true, false))) return rc;
-            CU(p, cudaEventRecord(p->ev_b, p->comm_stream));
-            if ((rc = launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, f, 0, st))) return rc;
-            if ((rc = p2p_signal_wait(p, st, false, true))) return rc;
-            CU(p, cudaStreamWaitEvent(st, p->ev_b, 0));          // H_own is free for the caller after this
-            return launch_spmm(p, p->halo, halo, nullptr, p->h, Z, nullptr, p->m, f, 1, st);
-        }
-        if ((rc = launch_pack(p, H_own, nullptr, dst, f, st))) return rc;
-        if ((rc = p2p_signal_wait(p, st, true, true))) return rc;
-        return launch_spmm(p, p->fwd, H_own, halo, p->m, Z, nullptr, p->m, f, 0, st);
+        par = (int)(p->epoch & 1);
+        halo = arena_ptr(p->arena, p->off_fwd[par]);
     }
-    if (!p->comm) return fail(p, PGCN_ERR_STATE, "k=%d: call pgcn_comm_init or pgcn_p2p_import first", p->k);
+    cudaStream_t cs = split ? p->comm_stream : st;
     if (split) {
-        // comm stream: pack -> all-to-all-v ; main stream: own-columns SpMM ; join ; halo-columns SpMM
         CU(p, cudaEventRecord(p->ev_a, st));
-        CU(p, cudaStreamWaitEvent(p->comm_stream, p->ev_a, 0));
-        if ((rc = launch_pack(p, H_own, p->d_send_slab, nullptr, f, p->comm_stream))) return rc;
-        if ((rc = nccl_exchange(p, p->d_send_slab, p->d_halo_slab, f, 0, p->comm_stream))) return rc;
-        CU(p, cudaEventRecord(p->ev_b, p->comm_stream));
-        if ((rc = launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, f, 0, st))) return rc;
-        CU(p, cudaStreamWaitEvent(st, p->ev_b, 0));
-        return launch_spmm(p, p->halo, p->d_halo_slab, nullptr, p->h, Z, nullptr, p->m, f, 1, st);
+        CU(p, cudaStreamWaitEvent(cs, p->ev_a, 0));
     }
-    if ((rc = launch_pack(p, H_own, p->d_send_slab, nullptr, f, st))) return rc;
-    if ((rc = nccl_exchange(p, p->d_send_slab, p->d_halo_slab, f, 0, st))) return rc;
-    return launch_spmm(p, p->fwd, H_own, p->d_halo_slab, p->m, Z, nullptr, p->m, f, 0, st);
+    // ---- send side (exchange stream): one peer after the other, in step order
+    if (use_p2p) {
+        for (int i = 1; i < k; ++i)
+            if ((rc = p2p_put(p, step_dst(p, i), H_own, f, false, par, cs))) return rc;
+        if (split) CU(p, cudaEventRecord(p->ev_b, cs));                   // H_own is free for the caller after this
+    } else {
+        if ((rc = launch_pack(p, H_own, p->d_send_slab, f, cs))) return rc;
+        for (int i = 1; i < k; ++i) {
+            if ((rc = nccl_step(p, p->d_send_slab, halo, f, 0, i, cs))) return rc;
+            if (split) CU(p, cudaEventRecord(p->ev_step[(size_t)i], cs));
+        }
+    }
+    if (!split) {
+        // no overlap requested (or nothing to split): wait for every block, then one pass over [own | halo]
+        if (use_p2p)
+            for (int i = 1; i < k; ++i)
+                if ((rc = p2p_wait(p, step_src(p, i), st))) return rc;
+        return launch_spmm(p, p->fwd, H_own, p->h > 0 ? halo : nullptr, p->m, Z, nullptr, p->m, f, 0, st);
+    }
+    // ---- compute side: own columns while the rows travel, then each source's block as soon as it has landed
+    if ((rc = launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, f, 0, st))) return rc;
+    for (int i = 1; i < k; ++i) {
+        const int src = step_src(p, i);
+        if (use_p2p) { if ((rc = p2p_wait(p, src, st))) return rc; }
+        else CU(p, cudaStreamWaitEvent(st, p->ev_step[(size_t)i], 0));
+        if (p->halo_q[(size_t)src].nrows == 0) continue;
+        if ((rc = launch_spmm(p, p->halo_q[(size_t)src], halo, nullptr, p->h, Z, nullptr, p->m, f, 1, st))) return rc;
+    }
+    if (use_p2p) CU(p, cudaStreamWaitEvent(st, p->ev_b, 0));
+    return 0;
 }
 
 int pgcn_backward(pgcn_plan* p, const float* gZ, float* G_own, int32_t f, void* stream)
@@ -1085,27 +1239,50 @@ int pgcn_backward(pgcn_plan* p, const float* gZ, float* G_own, int32_t f, void* 
     if (p->m > 0 && (!gZ || !G_own)) return fail(p, PGCN_ERR_INVALID, "null gZ/G_own");
     cudaStream_t st = (cudaStream_t)stream;
     // A^T g : rows [0,m) -> G_own, rows [m,m+h) -> halo partials, already in reverse wire order
-    if ((rc = launch_spmm(p, p->tr, gZ, nullptr, p->m, G_own, p->d_hsend_slab, p->m, f, 0, st))) return rc;
-    if (p->k == 1) return 0;
-    if (p->p2p && (f % 4 == 0)) {
+    if (p->k == 1) return launch_spmm(p, p->tr, gZ, nullptr, p->m, G_own, p->d_hsend_slab, p->m, f, 0, st);
+
+    const bool use_p2p = p->p2p && (f % 4 == 0);
+    if (!use_p2p && !p->comm) return fail(p, PGCN_ERR_STATE, "k=%d: call pgcn_comm_init or pgcn_p2p_import first", p->k);
+    const bool split = p->have_split && p->opt_overlap;
+    const int k = p->k;
+    float* rrecv = p->d_rrecv_slab;
+    int par = 0;
+    if (use_p2p) {
         ++p->epoch;
-        const int par = (int)(p->epoch & 1);
-        if (p->h > 0) {
-            PutArgs a;
-            a.src = p->d_hsend_slab; a.k = p->k; a.f = f;
-            for (int q = 0; q <= p->k; ++q) a.off[q] = p->recv_off[q];
-            for (int q = 0; q < p->k; ++q)
-                a.peer_dst[q] = arena_ptr(p->peer_arena[q], p->peer_blob[q].off_bwd[par]) + (size_t)p->peer_blob[q].send_off[p->rank] * f;
-            put_rows_kernel<<<grid_for((long long)p->h * (f / 4)), 256, 0, st>>>(a);
-            ++p->launches;
-            CU(p, cudaGetLastError());
-        }
-        if ((rc = p2p_signal_wait(p, st, true, true))) return rc;
-        return launch_unpack(p, arena_ptr(p->arena, p->off_bwd[par]), G_own, f, st);
+        par = (int)(p->epoch & 1);
+        rrecv = arena_ptr(p->arena, p->off_bwd[par]);
     }
-    if (!p->comm) return fail(p, PGCN_ERR_STATE, "k=%d: call pgcn_comm_init or pgcn_p2p_import first", p->k);
-    if ((rc = nccl_exchange(p, p->d_hsend_slab, p->d_rrecv_slab, f, 1, st))) return rc;
-    return launch_unpack(p, p->d_rrecv_slab, G_own, f, st);
+    if (!split) {
+        if ((rc = launch_spmm(p, p->tr, gZ, nullptr, p->m, G_own, p->d_hsend_slab, p->m, f, 0, st))) return rc;
+        for (int i = 1; i < k; ++i) {
+            if (use_p2p) { if ((rc = p2p_put(p, step_dst(p, i), p->d_hsend_slab, f, true, par, st))) return rc; }
+            else if ((rc = nccl_step(p, p->d_hsend_slab, rrecv, f, 1, i, st))) return rc;
+        }
+        if (use_p2p)
+            for (int i = 1; i < k; ++i)
+                if ((rc = p2p_wait(p, step_src(p, i), st))) return rc;
+        return launch_unpack(p, rrecv, G_own, f, st);
+    }
+    // ---- pipelined: the partials owed to each peer are computed first (in step order) and leave on the exchange
+    // stream while the next peer's rows, and finally the own rows of A^T g, are still being computed
+    cudaStream_t cs = p->comm_stream;
+    for (int i = 1; i < k; ++i) {
+        const int dst = step_dst(p, i);
+        if (p->tr_halo_q[(size_t)dst].nrows > 0)
+            if ((rc = launch_spmm(p, p->tr_halo_q[(size_t)dst], gZ, nullptr, p->m, G_own, p->d_hsend_slab, p->m, f, 0, st))) return rc;
+        CU(p, cudaEventRecord(p->ev_step[(size_t)i], st));
+        CU(p, cudaStreamWaitEvent(cs, p->ev_step[(size_t)i], 0));
+        if (use_p2p) { if ((rc = p2p_put(p, dst, p->d_hsend_slab, f, true, par, cs))) return rc; }
+        else if ((rc = nccl_step(p, p->d_hsend_slab, rrecv, f, 1, i, cs))) return rc;
+    }
+    CU(p, cudaEventRecord(p->ev_b, cs));
+    if ((rc = launch_spmm(p, p->tr_own, gZ, nullptr, p->m, G_own, p->d_hsend_slab, p->m, f, 0, st))) return rc;
+    if (use_p2p) {
+        for (int i = 1; i < k; ++i)
+            if ((rc = p2p_wait(p, step_src(p, i), st))) return rc;
+    }
+    CU(p, cudaStreamWaitEvent(st, p->ev_b, 0));      // NCCL: all blocks received; p2p: the send slab is free again
+    return launch_unpack(p, rrecv, G_own, f, st);
 }
 
 int pgcn_forward_host(pgcn_plan* p, const float* H_host, float* Z_host, int32_t f)

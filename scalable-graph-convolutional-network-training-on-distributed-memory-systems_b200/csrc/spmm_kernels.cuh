@@ -60,8 +60,6 @@ struct SpmmArgs {
     int beta;                // 0: Z = A*H ; 1: Z += A*H
 };
 
-constexpr int kMaxPeersDev = 16;
-
 template <int VW> struct Vec;
 template <> struct Vec<4> { typedef float4 type; };
 template <> struct Vec<1> { typedef float type; };
@@ -372,17 +370,13 @@ spmm_fixup_kernel(const FixupArgs a)
     }
 }
 
-// send_slab[j, :] = H[send_idx[j], :] ; when `peer_dst` is non-null the row goes straight into the
-// destination rank's halo slab through its NVLink-mapped address (fused pack + transport).
+// send_slab[j, :] = H[send_idx[j], :] for all peers in one launch (the staging copy of the NCCL transport and the
+// step-by-step entry point pgcn_pack; the peer-memory transport uses put_rows_kernel instead).
 struct PackArgs {
     const int* send_idx;       // S
     long long S;
     const float* H;
-    float* slab;               // local send slab (used when !to_peers)
-    long long send_off[kMaxPeersDev + 1];
-    float* peer_dst[kMaxPeersDev];   // base of "rows from me" inside peer p's halo slab
-    bool to_peers;
-    int k;
+    float* slab;
     int f;
 };
 
@@ -398,71 +392,68 @@ pack_rows_kernel(const PackArgs a)
         const long long j = t / nvec;
         const int v = (int)(t - j * nvec);
         const int src = __ldg(a.send_idx + j);
-        const vec_t val = ld_feat(reinterpret_cast<const vec_t*>(a.H + (size_t)src * a.f) + v);
-        if (!a.to_peers) {
-            reinterpret_cast<vec_t*>(a.slab + (size_t)j * a.f)[v] = val;
-        } else {
-            int p = 0;                                   // k is tiny: linear scan of the offsets
-            while (p + 1 < a.k && j >= a.send_off[p + 1]) ++p;
-            float* base = a.peer_dst[p];
-            reinterpret_cast<vec_t*>(base + (size_t)(j - a.send_off[p]) * a.f)[v] = val;
+        reinterpret_cast<vec_t*>(a.slab + (size_t)j * a.f)[v] =
+            ld_feat(reinterpret_cast<const vec_t*>(a.H + (size_t)src * a.f) + v);
+    }
+}
+
+// One destination of the peer-memory exchange, fused: gather (or copy) the rows that go to ONE peer, store them
+// straight into that peer's slab through its NVLink-mapped address, and publish the epoch flag once the last
+// CTA's stores are visible system-wide. No staging slab, no separate signal launch, and the receiver can start
+// on this peer's rows while the rows of the other peers are still in flight (Parallel-GCN/main.c:275-299:
+// MPI_Waitany -> accumulate per received block).
+//   forward : rows = H[send_idx[j0 .. j0+nrows)]      (GPU/PGCN.py:104 per peer)
+//   backward: rows = src[j0 .. j0+nrows) (halo partials of A^T g, already in wire order; send_idx == nullptr)
+struct PutArgs {
+    const int* send_idx;             // null: identity (row j0 + i of src)
+    long long j0, nrows;
+    const float* src;
+    float* dst;                      // "rows from me" inside the peer's slab
+    int f;
+    unsigned int* done;              // CTA completion counter of this destination (self-resetting)
+    unsigned long long* flag;        // peer's flag slot for me
+    unsigned long long epoch;
+};
+
+template <int VW>
+__global__ void __launch_bounds__(256)
+put_rows_kernel(const PutArgs a)
+{
+    typedef typename Vec<VW>::type vec_t;
+    const int nvec = a.f / VW;
+    const long long total = a.nrows * nvec;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long i = t / nvec;
+        const int v = (int)(t - i * nvec);
+        const long long srow = a.send_idx ? (long long)__ldg(a.send_idx + a.j0 + i) : a.j0 + i;
+        const vec_t val = ld_feat(reinterpret_cast<const vec_t*>(a.src + (size_t)srow * a.f) + v);
+        reinterpret_cast<vec_t*>(a.dst + (size_t)i * a.f)[v] = val;
+    }
+    // last CTA out publishes the epoch: every CTA fences its own stores system-wide before it counts itself
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int t = atomicAdd(a.done, 1u);
+        if (t == gridDim.x - 1) {
+            atomicExch(a.done, 0u);
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag), "l"(a.epoch) : "memory");
         }
     }
 }
 
-// Plain slab copy into peer memory (reverse direction: the halo partials are already in wire order).
-struct PutArgs {
-    const float* src;            // rows in wire order
-    long long off[kMaxPeersDev + 1];   // row offsets per destination
-    float* peer_dst[kMaxPeersDev];     // destination bases
-    int k; int f;
-};
-
-__global__ void __launch_bounds__(256)
-put_rows_kernel(const PutArgs a)
+// Spin until ONE peer's slot in my flag array has reached `epoch` (one tiny CTA: it never competes for SMs with
+// the kernels whose stores it waits for).
+__global__ void p2p_wait_kernel(const unsigned long long* flag, unsigned long long epoch)
 {
-    const int nvec = a.f / 4;                              // launcher guarantees f % 4 == 0
-    const long long total = a.off[a.k] * nvec;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        const long long j = t / nvec;
-        const int v = (int)(t - j * nvec);
-        int p = 0;
-        while (p + 1 < a.k && j >= a.off[p + 1]) ++p;
-        const float4 val = __ldcs(reinterpret_cast<const float4*>(a.src + (size_t)j * a.f) + v);
-        reinterpret_cast<float4*>(a.peer_dst[p] + (size_t)(j - a.off[p]) * a.f)[v] = val;
-    }
-}
-
-// Cross-GPU epoch flags for the peer-memory transport.
-// signal: after every store of this stream has been made visible system-wide, write `epoch`
-//         into slot [my_rank] of every peer's flag array.
-// wait  : spin until every peer's slot in MY flag array has reached `epoch`.
-struct FlagPtrs { unsigned long long* p[kMaxPeersDev]; };
-
-__global__ void p2p_signal_kernel(const FlagPtrs peer_flags, int k, int my_rank,
-                                  unsigned long long epoch)
-{
-    __threadfence_system();
-    const int p = threadIdx.x;
-    if (p < k && p != my_rank) {
-        unsigned long long* dst = peer_flags.p[p] + my_rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(epoch) : "memory");
-    }
-}
-
-__global__ void p2p_wait_kernel(const unsigned long long* my_flags, int k, int my_rank,
-                                unsigned long long epoch)
-{
-    const int p = threadIdx.x;
-    if (p < k && p != my_rank) {
+    if (threadIdx.x == 0) {
         unsigned long long v;
         do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(my_flags + p) : "memory");
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
         } while (v < epoch);
+        __threadfence_system();
     }
-    __syncthreads();
-    __threadfence_system();
 }
 
 // G[brow[i], :] += sum_{q in bpos[bptr[i] .. bptr[i+1])} recv[q, :], in list order.

@@ -94,8 +94,7 @@ __device__ __noinline__ void ring_store_row(float4 a0, float4 a1, const int* row
     }
 }
 
-constexpr int kRingWarps = 4;        // warps per CTA (each fully independent)
-constexpr int kRingG = 8;            // edges per completion group (= 1/4 of an index piece)
+constexpr int kRingWarps = 2;        // warps per CTA (each fully independent: CTA size only sets the smem granule)
 constexpr int kRingPieces = 4;       // index pieces (32 entries = 256 B each) per warp
 
 struct RingArgs {
@@ -105,34 +104,44 @@ struct RingArgs {
 };
 
 // per warp: NS row slots | NP index pieces | NS weights | NG + NP mbarriers
-__host__ __device__ constexpr size_t ring_warp_bytes(int vpl, int ns)
+__host__ __device__ constexpr size_t ring_warp_bytes(int vpl, int ns, int ng)
 {
     return ((size_t)ns * vpl * 512 + (size_t)kRingPieces * 256 + (size_t)ns * 4 +
-            (size_t)(ns / kRingG + kRingPieces) * 8 + 127) / 128 * 128;
+            (size_t)(ng + kRingPieces) * 8 + 127) / 128 * 128;
 }
-__host__ __device__ constexpr size_t ring_smem_bytes(int vpl, int ns) { return ring_warp_bytes(vpl, ns) * kRingWarps + 128; }
+__host__ __device__ constexpr size_t ring_smem_bytes(int vpl, int ns, int ng)
+{
+    return ring_warp_bytes(vpl, ns, ng) * kRingWarps + 128;
+}
 
-// VPL: 128-float vector groups per row (tile of f); NS: row slots per warp (16 or 32);
-// MODE 0: 1-D TMA bulk copies (UBLKCP + mbarrier), 1: per-lane 16-byte cp.async (LDGSTS + wait_group),
-// MODE 2: 2-D tensor-map TMA in tile::gather4 mode (UTMALDG.2D.GATHER4, four rows per instruction; groups that
-//         mix own and halo columns, or are cut by a block boundary, fall back to the 1-D copies of MODE 0).
+// VPL : 128-float vector groups per row (tile of f).
+// G   : edges per completion group (8, 16 or 32); NG: groups in the ring (2 or 4); the warp owns NS = G * NG row slots.
+// MODE: 0 = 1-D TMA bulk copies (UBLKCP, one per row), 1 = per-lane 16-byte cp.async (LDGSTS + wait_group),
+//       2 = 2-D tensor-map TMA in tile::gather4 mode (UTMALDG.2D.GATHER4, FOUR rows per instruction; quads that mix
+//           own and halo columns, or groups cut by a block boundary, fall back to the 1-D copies of MODE 0).
+// HALO: columns >= split live in a second matrix (the halo slab).
 //
 // The edge stream is walked in GLOBALLY ALIGNED units: a piece = entries [32 P, 32 P + 32) of the pair array (one
-// 256-byte bulk copy), a group = entries [8 g, 8 g + 8) (one completion unit of the row ring, slot group g % NG).
+// 256-byte bulk copy), a group = entries [G g, G g + G) (one completion unit of the row ring, slot group g % NG).
 // A row block [e0, e1) starts and ends anywhere; entries of its first / last group outside the block are masked.
-// Because everything is aligned, the loop body is one piece = four groups with STATIC slot numbers: consume group
-// (P, q), then issue the group NG positions ahead into the slots just freed. What travels from issue to
-// consumption lives in registers (row-end mask, valid mask per slot group) and in a tiny weight array.
-template <int VPL, int NS, int MODE>
+// Because everything is aligned, the loop body has STATIC slot numbers: consume group g, then issue group g + NG
+// into the slots just freed. What travels from issue to consumption lives in registers (row-end mask and valid
+// mask per slot group) and in a tiny weight array; per-group overhead (mbarrier arm / wait, masks) is amortised
+// over G edges, the gather4 issue over 4 rows per instruction.
+template <int VPL, int G, int NG, int MODE, bool HALO>
 __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra, const CUtensorMap* tm0, const CUtensorMap* tm1)
 {
-    constexpr int G = kRingG, NG = NS / G, NP = kRingPieces;
+    constexpr int NS = G * NG, NP = kRingPieces;
+    constexpr int PG = 32 / G;                                           // groups per index piece
+    constexpr int U = (NG > PG) ? NG / PG : 1;                           // pieces per loop body (body groups % NG == 0)
     constexpr uint32_t RB = VPL * 512;                                   // bytes of one row tile
-    static_assert(NG == 2 || NG == 4, "ring holds 2 or 4 groups of 8 rows");
+    constexpr uint32_t FULL = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+    static_assert((G == 8 || G == 16 || G == 32) && (NG == 2 || NG == 4), "unsupported ring shape");
+    static_assert((U * PG) % NG == 0, "slot groups must be static in the loop body");
     extern __shared__ __align__(128) unsigned char ring_smem[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* wbase = ring_smem + (size_t)warp * ring_warp_bytes(VPL, NS);
+    unsigned char* wbase = ring_smem + (size_t)warp * ring_warp_bytes(VPL, NS, NG);
     const uint32_t s_data = smem_u32(wbase);                             // NS slots of RB bytes
     const uint32_t s_idx = s_data + NS * RB;                             // NP pieces of 32 int2
     const uint32_t s_gbar = s_idx + NP * 256 + NS * 4;                   // NG group barriers
@@ -155,8 +164,8 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
     const size_t pitch = (size_t)a.f * 4;
     const size_t toff = (size_t)blockIdx.y * RB;
     const char* hb0 = reinterpret_cast<const char*>(a.H0) + toff;
-    const char* hb1 = reinterpret_cast<const char*>(a.H1) + toff - (size_t)a.split * pitch;   // halo slab, column-relative
-    const unsigned usplit = a.H1 ? (unsigned)a.split : 0xffffffffu;
+    const char* hb1 = HALO ? reinterpret_cast<const char*>(a.H1) + toff - (size_t)a.split * pitch : hb0;
+    const unsigned usplit = HALO ? (unsigned)a.split : 0xffffffffu;
     unsigned int* counter = ra.counter ? ra.counter + blockIdx.y : nullptr;
 
     uint32_t gpar = 0;                   // phase parity of each group barrier (bit sg)
@@ -178,8 +187,8 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
         const int lastmask = seg ? 0 : kLastFlag;
         const int e0 = b.z, e1 = b.w;
         int row = b.x;
-        const int gA = e0 >> 3, gB = (e1 - 1) >> 3;                      // first / last (aligned) group
-        const int P0 = gA >> 2, P1 = gB >> 2;                            // first / last piece
+        const int gA = e0 / G, gB = (e1 - 1) / G;                        // first / last (aligned) group
+        const int P0 = e0 >> 5, P1 = (e1 - 1) >> 5;                      // first / last piece
         uint32_t vmask[NG], emask[NG];                                   // per slot group: valid edges, row ends
 #pragma unroll
         for (int i = 0; i < NG; ++i) vmask[i] = emask[i] = 0;
@@ -210,38 +219,41 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
                 return;
             }
             int2 cw = make_int2(0, 0);
-            if (lane < G) cw = idx_gen[pslot * 32 + qs * 8 + lane];
+            if (lane < G) cw = idx_gen[pslot * 32 + qs * G + lane];
             bool valid = lane < G;
-            uint32_t vm = 0xffu;
+            uint32_t vm = FULL;
             if (gi == gA || gi == gB) {                                  // first / last group of the block: mask
-                const int e = gi * 8 + lane;
+                const int e = gi * G + lane;
                 valid = valid && e >= e0 && e < e1;
                 vm = __ballot_sync(0xffffffffu, valid);
             }
             emask[sg] = __ballot_sync(0xffffffffu, valid && (cw.x & lastmask));
             vmask[sg] = vm;
             if (lane < G) w_slot[sg * G + lane] = valid ? __int_as_float(cw.y) : 0.f;
-            const unsigned cj = (unsigned)(cw.x & kColMask);
-            const char* src = (cj >= usplit ? hb1 : hb0) + (size_t)cj * pitch;
-            const unsigned long long pol = (cw.x & kColdFlag) ? pol_cold : pol_hot;
             if (MODE == 0 || MODE == 2) {
                 if (lane == 0) mbar_expect_tx(s_gbar + sg * 8, (uint32_t)__popc(vm) * RB);
                 bool single = valid;                                     // this lane copies its own row (1-D bulk)
-                if (MODE == 2 && vm == 0xffu) {
-                    // lanes 0 and 1 look at the four columns of their quad (entries 4q .. 4q+3 of this group)
-                    const unsigned c0 = (unsigned)__shfl_sync(0xffffffffu, cw.x, (lane & 1) * 4 + 0);
-                    const unsigned c1 = (unsigned)__shfl_sync(0xffffffffu, cw.x, (lane & 1) * 4 + 1);
-                    const unsigned c2 = (unsigned)__shfl_sync(0xffffffffu, cw.x, (lane & 1) * 4 + 2);
-                    const unsigned c3 = (unsigned)__shfl_sync(0xffffffffu, cw.x, (lane & 1) * 4 + 3);
+                if (MODE == 2 && vm == FULL) {
+                    // lanes 0 .. G/4-1 each look at the four columns of one quad (entries 4 q .. 4 q + 3 of the group)
+                    const int qb = (lane & (G / 4 - 1)) * 4;
+                    const unsigned c0 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 0);
+                    const unsigned c1 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 1);
+                    const unsigned c2 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 2);
+                    const unsigned c3 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 3);
                     const unsigned r0 = c0 & kColMask, r1 = c1 & kColMask, r2 = c2 & kColMask, r3 = c3 & kColMask;
-                    const bool allown = r0 < usplit && r1 < usplit && r2 < usplit && r3 < usplit;
-                    const bool allhalo = r0 >= usplit && r1 >= usplit && r2 >= usplit && r3 >= usplit;
-                    const bool quad_ok = allown || allhalo;
-                    const uint32_t okmask = __ballot_sync(0xffffffffu, quad_ok) & 3u;
-                    single = valid && !((okmask >> (lane >> 2)) & 1);
+                    bool allhalo = false, quad_ok = true;
+                    if (HALO) {
+                        const bool allown = r0 < usplit && r1 < usplit && r2 < usplit && r3 < usplit;
+                        allhalo = r0 >= usplit && r1 >= usplit && r2 >= usplit && r3 >= usplit;
+                        quad_ok = allown || allhalo;
+                        const uint32_t okmask = __ballot_sync(0xffffffffu, quad_ok) & ((1u << (G / 4)) - 1u);
+                        single = valid && !((okmask >> (lane >> 2)) & 1);
+                    } else {
+                        single = false;
+                    }
                     __syncwarp();
-                    if (lane < 2 && quad_ok) {
-                        const unsigned sub = allhalo ? (unsigned)a.split : 0u;
+                    if (lane < G / 4 && quad_ok) {
+                        const unsigned sub = allhalo ? usplit : 0u;
                         const bool cold = (c0 & c1 & c2 & c3 & kColdFlag) != 0;
                         tma_gather4(s_data + (sg * G + lane * 4) * RB, allhalo ? tm1 : tm0, (int)(blockIdx.y * (RB / 4)),
                                     (int)(r0 - sub), (int)(r1 - sub), (int)(r2 - sub), (int)(r3 - sub),
@@ -250,8 +262,15 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
                 } else {
                     __syncwarp();
                 }
-                if (single) bulk_g2s(s_data + (sg * G + lane) * RB, src, RB, s_gbar + sg * 8, pol);
+                if (single) {
+                    const unsigned cj = (unsigned)(cw.x & kColMask);
+                    bulk_g2s(s_data + (sg * G + lane) * RB, (cj >= usplit ? hb1 : hb0) + (size_t)cj * pitch, RB,
+                             s_gbar + sg * 8, (cw.x & kColdFlag) ? pol_cold : pol_hot);
+                }
             } else {
+                const unsigned cj = (unsigned)(cw.x & kColMask);
+                const char* src = (cj >= usplit ? hb1 : hb0) + (size_t)cj * pitch;
+                const unsigned long long pol = (cw.x & kColdFlag) ? pol_cold : pol_hot;
 #pragma unroll
                 for (int j = 0; j < G; ++j) {
                     const unsigned long long sj = __shfl_sync(0xffffffffu, (unsigned long long)src, j);
@@ -283,26 +302,29 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
             else cp_async_wait<NG - 1>();
             const uint32_t em = emask[sg];
             const float4* slot = data_gen + (size_t)(sg * G) * (RB / 16);
-            if (vm == 0xffu) {
-                const float4 wa = *reinterpret_cast<const float4*>(w_slot + sg * G);
-                const float4 wb = *reinterpret_cast<const float4*>(w_slot + sg * G + 4);
-                const float w[G] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-                float4 r[G][VPL];
+            if (vm == FULL) {
 #pragma unroll
-                for (int j = 0; j < G; ++j)
+                for (int c = 0; c < G; c += 8) {                         // 8 rows at a time: 8 x LDS.128 in flight
+                    const float4 wa = *reinterpret_cast<const float4*>(w_slot + sg * G + c);
+                    const float4 wb = *reinterpret_cast<const float4*>(w_slot + sg * G + c + 4);
+                    const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                    float4 r[8][VPL];
 #pragma unroll
-                    for (int v = 0; v < VPL; ++v) r[j][v] = slot[j * (RB / 16) + v * 32];
-                if (em == 0) {                                           // no row ends inside: 8 x (LDS.128, 4 FFMA)
+                    for (int j = 0; j < 8; ++j)
 #pragma unroll
-                    for (int j = 0; j < G; ++j)
+                        for (int v = 0; v < VPL; ++v) r[j][v] = slot[(c + j) * (RB / 16) + v * 32];
+                    if (((em >> c) & 0xffu) == 0) {                      // no row end inside: 8 x (LDS.128, 4 FFMA)
 #pragma unroll
-                        for (int v = 0; v < VPL; ++v) vfma(acc[v], w[j], r[j][v]);
-                } else {
+                        for (int j = 0; j < 8; ++j)
 #pragma unroll
-                    for (int j = 0; j < G; ++j) {
+                            for (int v = 0; v < VPL; ++v) vfma(acc[v], w[j], r[j][v]);
+                    } else {
 #pragma unroll
-                        for (int v = 0; v < VPL; ++v) vfma(acc[v], w[j], r[j][v]);
-                        if (em >> j & 1) flush_row();
+                        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                            for (int v = 0; v < VPL; ++v) vfma(acc[v], w[j], r[j][v]);
+                            if (em >> (c + j) & 1) flush_row();
+                        }
                     }
                 }
             } else {                                                     // first / last group of a block
@@ -319,25 +341,32 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
             __syncwarp();                                                // every lane is done with these slots
         };
 
-        // prologue: index pieces in flight, first piece landed, first NG groups of it issued
+        // prologue: index pieces in flight, first piece landed, the first NG groups issued
 #pragma unroll
         for (int i = 0; i < NP; ++i) fetch_piece();
         wait_piece();
 #pragma unroll
-        for (int q = 0; q < NG; ++q) issue_group(4 * P0 + q, q, q);
-        if (NG == 4) fetch_piece();                                      // piece P0 fully issued: its slot is free
+        for (int i = 0; i < NG; ++i) {
+            if (i > 0 && i % PG == 0) {                                  // the ring spans more than one piece
+                fetch_piece();
+                if (P0 + i / PG <= P1) wait_piece();
+            }
+            if (P0 + i / PG <= P1) issue_group(PG * P0 + i, i % PG, i);
+            else { vmask[i] = 0; if (MODE == 1) cp_async_commit(); }
+        }
+        if (NG % PG == 0) fetch_piece();                                 // the last piece touched is fully issued
 
-        for (int P = P0; P <= P1; ++P) {
+        for (int P = P0; P <= P1; P += U) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int sg = q % NG;
+            for (int idx = 0; idx < U * PG; ++idx) {
+                const int sg = idx % NG;
                 consume_group(sg);
-                const int qi = (q + NG) % 4;                             // sub-group of the group NG ahead
-                const int Pi = P + (q + NG) / 4;                         // its piece
+                const int qi = (idx + NG) % PG;                          // sub-group of the group NG ahead
+                const int Pi = P + (idx + NG) / PG;                      // its piece
                 if (qi == 0 && Pi <= P1) wait_piece();                   // first group of a new piece
-                if (Pi <= P1) issue_group(4 * Pi + qi, qi, sg);
+                if (Pi <= P1) issue_group(PG * Pi + qi, qi, sg);
                 else { vmask[sg] = 0; if (MODE == 1) cp_async_commit(); }
-                if (qi == 3) fetch_piece();                              // that piece is fully issued now
+                if (qi == PG - 1) fetch_piece();                         // that piece is fully issued now
             }
         }
 
@@ -357,20 +386,20 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
     if (MODE == 1) cp_async_wait<0>();
 }
 
-template <int VPL, int NS, int MODE>
+template <int VPL, int G, int NG, int MODE, bool HALO>
 __global__ void __launch_bounds__(kRingWarps * 32)
 spmm_ring_kernel(const SpmmArgs a, const RingArgs ra)
 {
-    ring_body<VPL, NS, MODE>(a, ra, nullptr, nullptr);
+    ring_body<VPL, G, NG, MODE, HALO>(a, ra, nullptr, nullptr);
 }
 
 // gather4 variant: the tensor maps of H_own (tm0) and of the halo slab (tm1) travel as __grid_constant__ parameters
-template <int VPL, int NS>
+template <int VPL, int G, int NG, bool HALO>
 __global__ void __launch_bounds__(kRingWarps * 32)
 spmm_ring_g4_kernel(const SpmmArgs a, const RingArgs ra, const __grid_constant__ CUtensorMap tm0,
                     const __grid_constant__ CUtensorMap tm1)
 {
-    ring_body<VPL, NS, 2>(a, ra, &tm0, &tm1);
+    ring_body<VPL, G, NG, 2, HALO>(a, ra, &tm0, &tm1);
 }
 
 }  // namespace pgcn

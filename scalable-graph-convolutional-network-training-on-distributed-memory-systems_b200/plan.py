@@ -310,11 +310,19 @@ class PgcnPlan:
                 if int(ok.item()) == 1:
                     dist.barrier(group=group)
                     used = "p2p"
-            if used is None and transport == "p2p":
-                cabi.check(rc if rc < 0 else -5, self._h)
+            if used is None:
+                # not unanimous: a rank whose own import succeeded must not keep storing into peer slabs while
+                # the others talk NCCL (the job would hang) — switch the peer transport off everywhere
+                self.set_option("p2p", 0)
+                if transport == "p2p":
+                    cabi.check(rc if rc < 0 else -5, self._h)
         # the NCCL communicator is always created: it is the transport of the step-by-step entry points
         # (pgcn_exchange) and the fallback of the fused ones for widths the peer-store kernels do not take
         # (f % 4 != 0)
+        if used == "p2p" and transport == "p2p":
+            # explicitly peer-memory only (e.g. several ranks sharing one device, where NCCL cannot be set up):
+            # widths the peer-store kernels do not take (f % 4 != 0) then have no transport and raise
+            return used
         ident = torch.zeros(cabi.NCCL_ID_BYTES, dtype=torch.uint8)
         if self.lp.rank == 0:
             buf = C.create_string_buffer(cabi.NCCL_ID_BYTES)
@@ -336,6 +344,26 @@ class PgcnPlan:
         self.stats["recv_volume"] += int(in_rows)
         self.stats["send_nmsg"] += lp.k - 1
         self.stats["recv_nmsg"] += lp.k - 1
+
+
+def link_local_plans(plans):
+    """All ranks' plans live in THIS process (one GPU or several): wire their peer-memory transports to each other
+    directly — export every arena, import the k blobs into every plan (same-process peers are reached through plain
+    device pointers, no IPC). Used by the single-box tests and by smoke(); a multi-process job uses init_comm."""
+    import torch
+    k = len(plans)
+    blobs = []
+    for p in plans:
+        blob = C.create_string_buffer(cabi.P2P_HANDLE_BYTES)
+        with torch.cuda.device(p.device):
+            cabi.check(p._lib.pgcn_p2p_export(p.handle, blob), p._h)
+        blobs.append(blob.raw)
+    packed = b"".join(blobs)
+    for p in plans:
+        assert p.lp.k == k
+        with torch.cuda.device(p.device):
+            cabi.check(p._lib.pgcn_p2p_import(p.handle, packed), p._h)
+    return "p2p"
 
 
 def build_plan(A, partvec, rank, size, f_max, device=None):

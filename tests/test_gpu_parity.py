@@ -175,7 +175,9 @@ def test_schedule_options_do_not_change_results(opts):
     dict(kernel=5, ring_slots=32, ring_edges_per_block=100, ring_long_row=150),
     dict(kernel=5, persistent=1, ring_edges_per_block=256), dict(kernel=6, persistent=1, ring_slots=16, ring_edges_per_block=77),
     dict(kernel=6, ring_slots=32, ring_edges_per_block=4096),
-    dict(kernel=7), dict(kernel=7, ring_slots=16, ring_edges_per_block=90, persistent=1),
+    dict(kernel=7), dict(kernel=7, ring_slots=16, ring_edges_per_block=90, persistent=0),
+    dict(kernel=7, ring_slots=32, ring_edges_per_block=200), dict(kernel=7, ring_slots=64, ring_edges_per_block=300),
+    dict(kernel=7, ring_slots=64, ring_groups=4, ring_edges_per_block=64, ring_long_row=100), dict(kernel=5, ring_slots=32, persistent=0),
 ])
 def test_ring_kernel_matches_truth_and_register_kernel(f, opts):
     """The shared-memory ring SpMM (TMA bulk copies / cp.async into per-warp row slots): every ring depth,

@@ -137,10 +137,15 @@ def main():
         for epb, lr in itertools.product((64, 96, 128, 160, 192, 256, 384), (0, 100000)):
             point({"edges_per_block": epb, "tile_floats": 0, "long_row": lr})
     elif args.sweep == "ring":
-        # register pipeline (kernel 4) vs the shared-memory ring filled by TMA bulk copies (5) / cp.async (6)
+        # register pipeline (kernel 4) vs the shared-memory ring filled by 1-D TMA bulk copies (5) / cp.async (6) /
+        # TMA tile::gather4 (7); ring shapes: 16 slots (2 groups of 8), 32 (2 x 16), 64 (2 x 32 or 4 x 16)
         point({"kernel": 4})
-        for kern, slots, epb, pers in itertools.product((5, 6, 7), (16, 32), (256, 512, 1024), (0, 1)):
-            point({"kernel": kern, "ring_slots": slots, "ring_edges_per_block": epb, "persistent": pers})
+        for kern, (slots, groups), epb in itertools.product((7, 5), ((16, 2), (32, 2), (64, 2), (64, 4)), (256, 512, 1024)):
+            if kern == 5 and slots == 64:
+                continue
+            point({"kernel": kern, "ring_slots": slots, "ring_groups": groups, "ring_edges_per_block": epb, "persistent": 1})
+        point({"kernel": 7, "ring_slots": 32, "ring_groups": 2, "ring_edges_per_block": 512, "persistent": 0})
+        point({"kernel": 6, "ring_slots": 16, "ring_groups": 2, "ring_edges_per_block": 512, "persistent": 1})
     elif args.sweep == "ring-small":
         point({"kernel": 4})
         for kern, slots, epb, pers in ((5, 32, 1024, 0), (5, 16, 1024, 0), (5, 32, 2048, 1), (6, 32, 1024, 0), (6, 16, 1024, 0)):
