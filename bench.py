@@ -6,9 +6,12 @@
 
 metric  : aggregated edges/s of ONE layer's forward aggregation (PSpMM.forward = halo exchange +
           Z = A_local * H), whole job, = nnz(A^) / max-over-ranks time per step   (BASELINE.json metric)
-workload: BASELINE.json configs[1] — synthetic R-MAT 1 M vertices / 16 M edges (+ n self loops after
-          the reference preprocessing), f = 128, fp32. The same graph is split over N ranks for N > 1
-          (strong scaling; the 1-D row partition of GPU/PGCN.py with a part vector).
+workload: N = 1: BASELINE.json configs[1] (C2) — synthetic R-MAT 1 M vertices / 16 M edges (+ n self loops after
+          the reference preprocessing), f = 128, fp32.  N > 1: configs[4] (C5) — R-MAT 10 M / 100 M, f = 128, the
+          graph the north_star's scaling target is stated on, split over N ranks by the hypergraph part vector
+          shipped under bench_data/ (PaToH column-net model of GPU/hypergraph/main.cpp; tools/make_partvecs.py);
+          strong scaling, and rank 0 also times the SAME graph on its GPU alone (`single_gpu_same_config`) so the
+          speed-up can be read from one line. `--config` overrides either default.
 value   : device-resident inputs, CUDA-event timed, K steps after W warm-ups, max over ranks.
 e2e     : the same step through the C-ABI host entry point pgcn_forward_host — H in pinned HOST
           memory, copied in, aggregated, Z copied back, every step.
@@ -42,13 +45,37 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="C2")
+    ap.add_argument("--config", default=None, help="C2 | C3 | C4 | C5 (default: C2 on one GPU, C5 on several)")
     ap.add_argument("--partition", default="auto", help="auto | block | rp | path to a part vector")
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "p2p"])
     ap.add_argument("--cache", default=os.environ.get("PGCN_CACHE", "/tmp/pgcn_b200_cache"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lib-baseline", action="store_true")
+    ap.add_argument("--no-single", action="store_true", help="N > 1: skip the single-GPU run of the same config")
     ap.add_argument("--opt", action="append", default=[], help="plan option name=value (tuning)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.config is None:
+        args.config = "C2" if args.gpus <= 1 else "C5"
+    return args
+
+
+def workload_name(config):
+    """One string for both arms (the driver compares them)."""
+    from pgcn_b200 import graphio
+    n, nnz, f, _, _ = graphio.CONFIGS[config]
+    return ("%s: R-MAT %d vertices / %d edges (+%d self loops after A+I), f=%d, one forward aggregation "
+            "(halo exchange + Z=A_local*H) per step" % (config, n, nnz, n, f))
+
+
+def source_hash():
+    """sha1 over the kernel sources: profiles/traffic_<config>.json is only quoted when it was measured on this code."""
+    import hashlib
+    h = hashlib.sha1()
+    base = os.path.join(ROOT, "scalable-graph-convolutional-network-training-on-distributed-memory-systems_b200", "csrc")
+    for name in sorted(os.listdir(base)):
+        if name.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(base, name), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def peaks():
@@ -118,11 +145,15 @@ def part_vector(args, n, k):
     from pgcn_b200 import graphio
     if k == 1:
         return np.zeros(n, dtype=np.int64), "single part"
-    if args.partition not in ("auto", "block", "rp"):
+    if args.partition not in ("auto", "block", "rp", "hp", "gp"):
         return graphio.read_partvec(args.partition, n), os.path.basename(args.partition)
-    shipped = os.path.join(ROOT, "bench_data", "%s.%d.hp.npz" % (args.config, k))
-    if args.partition == "auto" and os.path.exists(shipped):
-        return np.load(shipped)["partvec"].astype(np.int64), "hp (PaToH column-net via the reference driver, precomputed)"
+    for method, what in (("hp", "hp (PaToH column-net hypergraph model of GPU/hypergraph/main.cpp, precomputed: bench_data/)"),
+                         ("gp", "gp (METIS k-way of GPU/graph/main.cpp, precomputed: bench_data/)")):
+        shipped = os.path.join(ROOT, "bench_data", "%s.%d.%s.npz" % (args.config, k, method))
+        if args.partition in ("auto", method) and os.path.exists(shipped):
+            return np.load(shipped)["partvec"].astype(np.int64), what
+    if args.partition in ("hp", "gp"):
+        raise SystemExit("no bench_data/%s.%d.%s.npz (tools/make_partvecs.py makes it)" % (args.config, k, args.partition))
     if args.partition == "rp":
         return graphio.random_partvec(n, k, seed=1), "rp (uniform random, seed 1)"
     return graphio.block_partvec(n, k), "block (contiguous vertex ranges)"
@@ -156,6 +187,37 @@ def cpu_baseline(lp, f, budget_s=20.0):
             "ms_per_pass": t * 1e3}
 
 
+def lib_baseline(A, H, n, nnz_total):
+    """What the reference would do on this very GPU, outside every timed region of the repo arm:
+    torch.sparse.mm on its uncoalesced int64 COO exactly as GPU/PGCN.py:60-63,127 builds and calls it, and the same
+    product on a prebuilt CSR (cuSPARSE). Library kernels — a baseline, not part of the product path."""
+    import torch
+    dev = H.device
+
+    def timed(fn, iters, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    idx = torch.from_numpy(np.vstack([A.row, A.col]).astype(np.int64)).to(dev)
+    val = torch.from_numpy(A.data.astype(np.float32)).to(dev)
+    coo = torch.sparse_coo_tensor(idx, val, (n, n))
+    ms_coo = timed(lambda: torch.sparse.mm(coo, H), 3, 1)
+    csr = coo.coalesce().to_sparse_csr()
+    ms_csr = timed(lambda: torch.sparse.mm(csr, H), 10, 2)
+    return {"reference_call_coo": {"ms": ms_coo, "value": nnz_total / (ms_coo * 1e-3), "unit": UNIT,
+                                   "what": "torch.sparse.mm on the uncoalesced int64 COO of GPU/PGCN.py:60-63,127"},
+            "cusparse_csr": {"ms": ms_csr, "value": nnz_total / (ms_csr * 1e-3), "unit": UNIT,
+                             "what": "torch.sparse.mm on a prebuilt CSR (cuSPARSE)"}}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU aggregation (C/OpenMP restatement of the GraphBLAS path)
     on the host cores, rank 0 only, one step = one full pass over the workload."""
@@ -185,7 +247,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: R-MAT %d vertices / %d edges (+%d self loops), f=%d, one forward aggregation" % (args.config, n, nnz, n, f)},
+        "config": {"workload": workload_name(args.config)},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "full workload per step; C/OpenMP restatement of Parallel-GCN/main.c:271,295 "
                                    "(SuiteSparse:GraphBLAS + MPI not buildable offline)"},
@@ -232,6 +294,7 @@ def main():
     pv, pv_name = part_vector(args, n, world)
     lp = planmod.build_local_plan(A, pv, rank, world)
     nnz_total = int(A.nnz)
+    keep_A = A if (rank == 0 and ((world > 1 and not args.no_single) or (world == 1 and not args.no_lib_baseline))) else None
     del A
     plan = planmod.PgcnPlan(lp, f, device=device)
     tuned = plan.autotune(f)          # set-up, untimed: like the reference's plan building
@@ -303,31 +366,75 @@ def main():
     sync_all()
     ms_bwd = b0.elapsed_time(b1) / nb
 
-    # ---- e2e: host buffers through the C-ABI host entry point ---------------------------------
-    Hh = torch.empty((lp.m, f), dtype=torch.float32).pin_memory()
-    Hh.copy_(H)
-    Zh = torch.empty((lp.m, f), dtype=torch.float32).pin_memory()
-    n_e2e = max(3, min(args.steps, 10))
+    # ---- e2e: host buffers through the C-ABI host entry points (software-pipelined: two device slots, the upload
+    # of step i+1 and the download of step i-1 run under the aggregation of step i; every step's H goes host ->
+    # device and every step's Z device -> host inside the timed region) --------------------------------------
+    Hh = [torch.empty((lp.m, f), dtype=torch.float32).pin_memory() for _ in range(2)]
+    Zh = [torch.empty((lp.m, f), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for x in Hh:
+        x.copy_(H)
+    n_e2e = max(4, min(args.steps, 12))
 
-    def e2e_step():
-        cabi.check(lib.pgcn_forward_host(plan.handle, Hh.data_ptr(), Zh.data_ptr(), f), plan.handle)
+    def e2e_run(nsteps):
+        for i in range(nsteps):
+            cabi.check(lib.pgcn_forward_host_async(plan.handle, Hh[i & 1].data_ptr(), Zh[i & 1].data_ptr(), f), plan.handle)
+        cabi.check(lib.pgcn_forward_host_wait(plan.handle), plan.handle)
 
-    e2e_step()
+    e2e_run(2)
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        e2e_step()
+    e2e_run(n_e2e)
     sync_all()
     s_e2e = (time.perf_counter() - t0) / n_e2e
+    # the strictly serial form (one step at a time: copy in, aggregate, copy out, synchronise)
+    t0 = time.perf_counter()
+    for i in range(3):
+        cabi.check(lib.pgcn_forward_host(plan.handle, Hh[0].data_ptr(), Zh[0].data_ptr(), f), plan.handle)
+    sync_all()
+    s_e2e_serial = (time.perf_counter() - t0) / 3
+    e2e_ok = bool(torch.equal(Zh[0], Zh[1])) and bool(torch.isfinite(Zh[0][:16]).all())
+    del Hh, Zh
 
     # ---- reduce over ranks ---------------------------------------------------------------------
-    vec = torch.tensor([ms, ms_kernel, ms_bwd, s_e2e * 1e3], device=device, dtype=torch.float64)
+    vec = torch.tensor([ms, ms_kernel, ms_bwd, s_e2e * 1e3, s_e2e_serial * 1e3, float(lp.h), float(lp.nnz())],
+                       device=device, dtype=torch.float64)
     tot = torch.tensor([float(launches), float(plan.algorithmic_bytes(f)["spmm_fwd"]), float(lp.m * f * 4),
                         float(plan.algorithmic_bytes(f)["xchg_in"])], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms, ms_kernel, ms_bwd, ms_e2e = [float(x) for x in vec.tolist()]
+    ms, ms_kernel, ms_bwd, ms_e2e, ms_e2e_serial, h_max, nnz_max = [float(x) for x in vec.tolist()]
+
+    # ---- N > 1: the same graph on ONE GPU (rank 0 alone, the others wait), so the line carries its own baseline
+    single = None
+    if world > 1 and not args.no_single:
+        if rank == 0:
+            try:
+                lp1 = planmod.build_local_plan(keep_A, np.zeros(n, dtype=np.int64), 0, 1)
+                p1 = planmod.PgcnPlan(lp1, f, device=device)
+                p1.autotune(f)
+                H1 = torch.rand((n, f), device=device) * 2 - 1
+                Z1 = torch.empty((n, f), device=device)
+                for _ in range(3):
+                    cabi.check(lib.pgcn_forward(p1.handle, H1.data_ptr(), Z1.data_ptr(), f, stream), p1.handle)
+                torch.cuda.synchronize()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ns = max(5, min(args.steps, 20))
+                s0.record()
+                for _ in range(ns):
+                    cabi.check(lib.pgcn_forward(p1.handle, H1.data_ptr(), Z1.data_ptr(), f, stream), p1.handle)
+                s1.record()
+                torch.cuda.synchronize()
+                ms1 = s0.elapsed_time(s1) / ns
+                b1 = p1.algorithmic_bytes(f)["spmm_fwd"]
+                single = {"ms_per_step": ms1, "value": nnz_total / (ms1 * 1e-3), "unit": UNIT, "steps": ns,
+                          "roofline_frac": b1 / (ms1 * 1e-3) / 1e9 / peaks()[0]}
+                p1.close()
+                del H1, Z1, lp1
+            except Exception as e:                      # never lose the multi-GPU number over the extra
+                single = {"error": str(e)[:200]}
+        dist.barrier()
+    keep_A_local = keep_A
     launches_all, bytes_all, h2d_all, xchg_all = [float(x) for x in tot.tolist()]
 
     if rank == 0:
@@ -345,8 +452,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "%s: R-MAT %d vertices / %d edges (+%d self loops after A+I), f=%d, one forward aggregation "
-                            "(halo exchange + Z=A_local*H) per step" % (args.config, n, nnz, n, f),
+                "workload": workload_name(args.config),
                 "partition": pv_name, "transport": transport, "l2": "inputs larger than L2 (H and Z %.0f MB each per rank)" % (lp.m * f * 4 / 1e6),
                 "plan_options": {k_: plan.get_option(k_) for k_ in ("edges_per_block", "long_row", "tile_floats", "overlap")},
                 "nnz": nnz_total, "halo_rows_rank0": int(lp.h), "send_rows_rank0": int(lp.S),
@@ -356,16 +462,37 @@ def main():
                          "algorithmic_bytes_per_launch": bytes_per_rank, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": nnz_total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),
-                    "d2h_bytes_per_step": int(h2d_all), "ms_per_step": ms_e2e, "api": "pgcn_forward_host (C-ABI, pinned host buffers)"},
+                    "d2h_bytes_per_step": int(h2d_all), "ms_per_step": ms_e2e,
+                    "api": "pgcn_forward_host_async + pgcn_forward_host_wait (C-ABI, pinned host buffers, two device slots: "
+                           "step i+1 uploads and step i-1 downloads under the aggregation of step i)",
+                    "steps": n_e2e, "serial_ms_per_step": ms_e2e_serial, "serial_api": "pgcn_forward_host", "results_equal": e2e_ok},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "backward": {"ms_per_step": ms_bwd, "value": nnz_total / (ms_bwd * 1e-3), "unit": UNIT},
             "exchange_bytes_in_per_step": int(xchg_all),
+            "per_rank": {"halo_rows_max": int(h_max), "nnz_max": int(nnz_max), "spmm_alone_ms_max": ms_kernel,
+                         "exchange_visible_ms": max(ms - ms_kernel, 0.0)},
         }
-        traffic_file = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.config)
-        if os.path.exists(traffic_file):
+        if single is not None:
+            line["single_gpu_same_config"] = single
+            if "value" in single:
+                line["speedup_vs_single_gpu"] = line["value"] / single["value"]
+        if world == 1 and not args.no_lib_baseline and keep_A_local is not None:
             try:
-                line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+                line["lib_baseline"] = lib_baseline(keep_A_local, H, n, nnz_total)
+            except Exception as e:
+                line["lib_baseline"] = {"error": str(e)[:200]}
+        # DRAM bytes per launch of the dominant kernel come from an ncu capture (tools/update_traffic.py); the file is
+        # stamped with the hash of the kernel sources it was measured on and ignored when the code has moved on
+        traffic_file = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.config)
+        if os.path.exists(traffic_file) and world == 1:
+            try:
+                tj = json.load(open(traffic_file))
+                if tj.get("source_hash") == source_hash():
+                    line["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
+                    line["roofline"]["traffic_source"] = "ncu dram__bytes_read+write per launch, %s" % tj.get("kernel", "")
+                else:
+                    line["roofline"]["traffic_source"] = "profiles/traffic_%s.json is stale (measured on other kernel sources)" % args.config
             except Exception:
                 pass
         print(json.dumps(line), flush=True)

@@ -201,6 +201,18 @@ int pgcn_backward(pgcn_plan* plan, const float* gZ, float* G_own, int32_t f, voi
  * device, runs the path, copies Z back, synchronises. This is the call bench.py times as "e2e".
  */
 int pgcn_forward_host(pgcn_plan* plan, const float* H_host, float* Z_host, int32_t f);
+/*
+ * Software-pipelined form for a host that streams many aggregations (layers, mini-batches, timesteps):
+ * pgcn_forward_host_async enqueues  H_host -> device slot (copy-in stream) ; pgcn_forward (compute stream) ;
+ * device slot -> Z_host (copy-out stream)  on one of TWO device slots and returns at once, so the upload of
+ * step i+1 and the download of step i-1 run under the aggregation of step i (PCIe is full duplex).
+ * H_host must stay untouched and Z_host unread until pgcn_forward_host_wait returns; it waits for everything
+ * enqueued so far. Pinned host buffers are needed for the copies to overlap. Replaces nothing in the reference
+ * (it has no host-resident path, GPU/PGCN.py:186-196 keeps H on the device): it is the C-trainer-facing form of
+ * the PSpMM.forward boundary (GPU/PGCN.py:123-127).
+ */
+int pgcn_forward_host_async(pgcn_plan* plan, const float* H_host, float* Z_host, int32_t f);
+int pgcn_forward_host_wait(pgcn_plan* plan);
 
 #ifdef __cplusplus
 }

@@ -167,8 +167,11 @@ struct pgcn_plan {
     P2PBlob peer_blob[kMaxPeers];
     unsigned long long epoch = 0;
 
-    // host-buffer variant
-    float* d_hostH = nullptr; float* d_hostZ = nullptr; int64_t host_cap = 0;
+    // host-buffer variant: two device slots, copy-in / compute / copy-out streams chained by events
+    float* d_hostH[2] = {nullptr, nullptr}; float* d_hostZ[2] = {nullptr, nullptr}; int64_t host_cap = 0;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    int64_t host_steps = 0;
 
     int64_t launches = 0;
     std::string err;
@@ -869,7 +872,15 @@ int pgcn_plan_destroy(pgcn_plan* p)
     cudaFree(p->d_send_idx);
     cudaFree(p->d_brow); cudaFree(p->d_bptr); cudaFree(p->d_bpos);
     cudaFree(p->d_send_slab); cudaFree(p->d_halo_slab); cudaFree(p->d_rrecv_slab); cudaFree(p->d_hsend_slab);
-    cudaFree(p->d_hostH); cudaFree(p->d_hostZ); cudaFree(p->d_counter);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(p->d_hostH[i]); cudaFree(p->d_hostZ[i]);
+        if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+        if (p->ev_comp[i]) cudaEventDestroy(p->ev_comp[i]);
+        if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
+    }
+    if (p->s_in) cudaStreamDestroy(p->s_in);
+    if (p->s_out) cudaStreamDestroy(p->s_out);
+    cudaFree(p->d_counter);
     if (p->comm_stream) cudaStreamDestroy(p->comm_stream);
     if (p->host_stream) cudaStreamDestroy(p->host_stream);
     if (p->ev_a) cudaEventDestroy(p->ev_a);
@@ -883,6 +894,13 @@ int pgcn_plan_set_option(pgcn_plan* p, const char* name, int64_t value)
 {
     if (!p || !name) return fail(p, PGCN_ERR_INVALID, "null argument");
     const std::string n(name);
+    auto clear_tuned = [&]() {
+        DevCsr* all[] = {&p->fwd, &p->tr, &p->own, &p->tr_own};
+        for (DevCsr* c : all) { c->tuned_epb[0] = c->tuned_epb[1] = 0; c->tuned_slots = 0; }
+        for (auto& c : p->halo_q) { c.tuned_epb[0] = c.tuned_epb[1] = 0; c.tuned_slots = 0; }
+        for (auto& c : p->tr_halo_q) { c.tuned_epb[0] = c.tuned_epb[1] = 0; c.tuned_slots = 0; }
+    };
+    if (n == "edges_per_block" || n == "ring_edges_per_block" || n == "ring_slots") clear_tuned();   // explicit beats tuned
     if (n == "edges_per_block") p->opt_epb = value;
     else if (n == "kernel") p->opt_kernel = value;
     else if (n == "ring_slots") p->opt_ring_slots = value;
@@ -892,7 +910,10 @@ int pgcn_plan_set_option(pgcn_plan* p, const char* name, int64_t value)
     else if (n == "ring_groups") p->opt_ring_groups = value;
     else if (n == "long_row") p->opt_long = value;
     else if (n == "tile_floats") p->opt_tile = value;
-    else if (n == "hot_mb") p->opt_hot_mb = value;
+    else if (n == "hot_mb")
+        // the cold-column marks are baked into the pair arrays at pgcn_plan_create: a later change would be a
+        // silent no-op, so it is refused (use the PGCN_HOT_MB environment variable before creating the plan)
+        return fail(p, PGCN_ERR_STATE, "hot_mb is fixed at plan creation (set PGCN_HOT_MB before pgcn_plan_create)");
     else if (n == "overlap") p->opt_overlap = value;
     else if (n == "p2p") {
         // 0 = never use the peer transport even though pgcn_p2p_import succeeded here (another rank could not map
@@ -908,10 +929,10 @@ int64_t pgcn_plan_get_option(const pgcn_plan* p, const char* name)
 {
     if (!p || !name) return PGCN_ERR_INVALID;
     const std::string n(name);
-    if (n == "edges_per_block") return p->opt_epb;
+    if (n == "edges_per_block") return p->fwd.tuned_epb[0] > 0 ? p->fwd.tuned_epb[0] : p->opt_epb;
     if (n == "kernel") return p->opt_kernel;
-    if (n == "ring_slots") return p->opt_ring_slots;
-    if (n == "ring_edges_per_block") return p->opt_ring_epb;
+    if (n == "ring_slots") return p->fwd.tuned_slots > 0 ? p->fwd.tuned_slots : p->opt_ring_slots;
+    if (n == "ring_edges_per_block") return p->fwd.tuned_epb[1] > 0 ? p->fwd.tuned_epb[1] : p->opt_ring_epb;
     if (n == "ring_long_row") return p->opt_ring_long;
     if (n == "persistent") return p->opt_persistent;
     if (n == "ring_groups") return p->opt_ring_groups;
@@ -947,48 +968,84 @@ int64_t pgcn_debug_schedule(const int32_t* rowptr, int32_t nrows, int64_t edges_
     return (int64_t)blocks.size();
 }
 
+// Autotune: every matrix of the plan (forward, transposed, and — for k > 1 — the own-column part, each peer's halo
+// block and the transposed row ranges the pipelined backward launches) gets its own schedule parameters, timed on
+// zero-filled scratch operands of the right shapes. Returns the edges-per-block chosen for the forward matrix.
 int pgcn_plan_autotune(pgcn_plan* p, int32_t f)
 {
     int rc = check_f(p, f);
     if (rc) return rc;
     if (p->fwd.nnz == 0) return (int)p->opt_epb;
     CU(p, cudaSetDevice(p->device));
-    float *H0 = nullptr, *H1 = nullptr, *Z = nullptr;
+    float *H0 = nullptr, *H1 = nullptr, *Z0 = nullptr, *Z1 = nullptr;
     const size_t bm = std::max<size_t>((size_t)p->m * f, 1) * 4, bh = std::max<size_t>((size_t)p->h * f, 1) * 4;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     auto cleanup = [&]() {
-        cudaFree(H0); cudaFree(H1); cudaFree(Z);
+        cudaFree(H0); cudaFree(H1); cudaFree(Z0); cudaFree(Z1);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
     };
     if (cudaMalloc((void**)&H0, bm) != cudaSuccess || cudaMalloc((void**)&H1, bh) != cudaSuccess ||
-        cudaMalloc((void**)&Z, bm) != cudaSuccess) {
+        cudaMalloc((void**)&Z0, bm) != cudaSuccess || cudaMalloc((void**)&Z1, bh) != cudaSuccess) {
         cleanup(); cudaGetLastError();
         return fail(p, PGCN_ERR_CUDA, "autotune: scratch allocation failed");
     }
-    cudaMemsetAsync(H0, 0, bm, p->host_stream); cudaMemsetAsync(H1, 0, bh, p->host_stream);
+    cudaStream_t st = p->host_stream;
+    cudaMemsetAsync(H0, 0, bm, st); cudaMemsetAsync(H1, 0, bh, st);
+    cudaMemsetAsync(Z0, 0, bm, st); cudaMemsetAsync(Z1, 0, bh, st);
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    static const int cand[] = {96, 112, 128, 144, 160, 192, 256};
-    const int64_t keep_epb = p->opt_epb;
-    int best = (int)keep_epb;
-    float best_ms = 1e30f;
-    for (int c : cand) {
-        p->opt_epb = c;
-        float ms_min = 1e30f;
-        for (int it = 0; it < 4; ++it) {                 // first pass also builds the schedule
-            cudaEventRecord(e0, p->host_stream);
-            rc = launch_spmm(p, p->fwd, H0, p->h ? H1 : nullptr, p->m, Z, nullptr, p->m, f, 0, p->host_stream);
-            cudaEventRecord(e1, p->host_stream);
-            if (rc || cudaEventSynchronize(e1) != cudaSuccess) { cleanup(); p->opt_epb = keep_epb; return rc ? rc : fail(p, PGCN_ERR_CUDA, "autotune: kernel failed"); }
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, e0, e1);
-            if (it > 0) ms_min = std::min(ms_min, ms);
+
+    struct Cand { int64_t epb; int slots; };
+    static const Cand ring_cand[] = {{256, 16}, {512, 16}, {1024, 16}, {512, 32}, {1024, 32}};
+    static const Cand reg_cand[] = {{96, 0}, {128, 0}, {144, 0}, {160, 0}, {192, 0}, {256, 0}};
+    // one matrix: h0/h1/split = gathered operand(s), z0/z1/zsplit = outputs
+    auto tune = [&](DevCsr& c, const float* h0, const float* h1, int split, float* z0, float* z1, int zsplit, int beta) -> int {
+        if (c.nnz == 0 || c.nrows == 0) return 0;
+        const bool ring = use_ring(p, h0, h1, f);
+        const Cand* cand = ring ? ring_cand : reg_cand;
+        const int ncand = ring ? (int)(sizeof ring_cand / sizeof ring_cand[0]) : (int)(sizeof reg_cand / sizeof reg_cand[0]);
+        const int which = ring ? 1 : 0;
+        const int64_t keep_epb = c.tuned_epb[which];
+        const int keep_slots = c.tuned_slots;
+        int best = -1;
+        float best_ms = 1e30f;
+        for (int i = 0; i < ncand; ++i) {
+            c.tuned_epb[which] = cand[i].epb;
+            if (ring) c.tuned_slots = cand[i].slots;
+            float ms_min = 1e30f;
+            for (int it = 0; it < 4; ++it) {                 // first pass also builds the schedule
+                cudaEventRecord(e0, st);
+                int r2 = launch_spmm(p, c, h0, h1, split, z0, z1, zsplit, f, beta, st);
+                cudaEventRecord(e1, st);
+                if (r2 || cudaEventSynchronize(e1) != cudaSuccess) {
+                    c.tuned_epb[which] = keep_epb; c.tuned_slots = keep_slots;
+                    return r2 ? r2 : fail(p, PGCN_ERR_CUDA, "autotune: kernel failed");
+                }
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (it > 0) ms_min = std::min(ms_min, ms);
+            }
+            if (ms_min < best_ms) { best_ms = ms_min; best = i; }
         }
-        if (ms_min < best_ms) { best_ms = ms_min; best = c; }
+        c.tuned_epb[which] = cand[best].epb;
+        if (ring) c.tuned_slots = cand[best].slots;
+        return 0;
+    };
+#define TUNE(...) do { if ((rc = tune(__VA_ARGS__))) { cleanup(); return rc; } } while (0)
+    TUNE(p->fwd, H0, p->h ? H1 : nullptr, p->m, Z0, nullptr, p->m, 0);
+    TUNE(p->tr, H0, nullptr, p->m, Z0, Z1, p->m, 0);
+    if (p->have_split) {
+        TUNE(p->own, H0, nullptr, p->m, Z0, nullptr, p->m, 0);
+        TUNE(p->tr_own, H0, nullptr, p->m, Z0, Z1, p->m, 0);
+        for (int q = 0; q < p->k; ++q) {
+            TUNE(p->halo_q[(size_t)q], H1, nullptr, p->h, Z0, nullptr, p->m, 1);
+            TUNE(p->tr_halo_q[(size_t)q], H0, nullptr, p->m, Z0, Z1, p->m, 0);
+        }
     }
-    p->opt_epb = best;
+#undef TUNE
     cleanup();
-    return best;
+    const int which = use_ring(p, H0, nullptr, f) ? 1 : 0;     // H0 was cudaMalloc'ed: aligned
+    return (int)(p->fwd.tuned_epb[which] > 0 ? p->fwd.tuned_epb[which] : (which ? p->opt_ring_epb : p->opt_epb));
 }
 
 void* pgcn_plan_slab(pgcn_plan* p, int which)
@@ -1285,25 +1342,76 @@ int pgcn_backward(pgcn_plan* p, const float* gZ, float* G_own, int32_t f, void* 
     return launch_unpack(p, rrecv, G_own, f, st);
 }
 
-int pgcn_forward_host(pgcn_plan* p, const float* H_host, float* Z_host, int32_t f)
+static int host_slots(pgcn_plan* p, int64_t need)
+{
+    if (!p->s_in) {
+        CU(p, cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+        CU(p, cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(p, cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+            CU(p, cudaEventCreateWithFlags(&p->ev_comp[i], cudaEventDisableTiming));
+            CU(p, cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    if (need > p->host_cap) {
+        CU(p, cudaDeviceSynchronize());
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(p->d_hostH[i]); cudaFree(p->d_hostZ[i]);
+            p->d_hostH[i] = p->d_hostZ[i] = nullptr;
+        }
+        p->host_cap = 0;
+        for (int i = 0; i < 2; ++i) {
+            CU(p, cudaMalloc((void**)&p->d_hostH[i], std::max<size_t>((size_t)need, 1) * 4));
+            CU(p, cudaMalloc((void**)&p->d_hostZ[i], std::max<size_t>((size_t)need, 1) * 4));
+        }
+        p->host_cap = need;
+        p->host_steps = 0;
+    }
+    return 0;
+}
+
+int pgcn_forward_host_async(pgcn_plan* p, const float* H_host, float* Z_host, int32_t f)
 {
     int rc = check_f(p, f);
     if (rc) return rc;
     if (p->m > 0 && (!H_host || !Z_host)) return fail(p, PGCN_ERR_INVALID, "null host buffer");
+    CU(p, cudaSetDevice(p->device));
     const int64_t need = (int64_t)p->m * f;
-    if (need > p->host_cap) {
-        cudaFree(p->d_hostH); cudaFree(p->d_hostZ);
-        p->d_hostH = p->d_hostZ = nullptr; p->host_cap = 0;
-        CU(p, cudaMalloc((void**)&p->d_hostH, std::max<size_t>((size_t)need, 1) * 4));
-        CU(p, cudaMalloc((void**)&p->d_hostZ, std::max<size_t>((size_t)need, 1) * 4));
-        p->host_cap = need;
-    }
-    cudaStream_t st = p->host_stream;   // plan-owned non-blocking stream
-    CU(p, cudaMemcpyAsync(p->d_hostH, H_host, (size_t)need * 4, cudaMemcpyHostToDevice, st));
-    if ((rc = pgcn_forward(p, p->d_hostH, p->d_hostZ, f, st))) return rc;
-    CU(p, cudaMemcpyAsync(Z_host, p->d_hostZ, (size_t)need * 4, cudaMemcpyDeviceToHost, st));
-    CU(p, cudaStreamSynchronize(st));
+    if ((rc = host_slots(p, need))) return rc;
+    const int s = (int)(p->host_steps & 1);
+    const bool reuse = p->host_steps >= 2;
+    cudaStream_t cs = p->host_stream;
+    // copy-in: the slot's H is free once the aggregation two steps ago has read it
+    if (reuse) CU(p, cudaStreamWaitEvent(p->s_in, p->ev_comp[s], 0));
+    CU(p, cudaMemcpyAsync(p->d_hostH[s], H_host, (size_t)need * 4, cudaMemcpyHostToDevice, p->s_in));
+    CU(p, cudaEventRecord(p->ev_in[s], p->s_in));
+    // compute: needs this step's H, and the slot's Z must have left for the host (two steps ago)
+    CU(p, cudaStreamWaitEvent(cs, p->ev_in[s], 0));
+    if (reuse) CU(p, cudaStreamWaitEvent(cs, p->ev_out[s], 0));
+    if ((rc = pgcn_forward(p, p->d_hostH[s], p->d_hostZ[s], f, cs))) return rc;
+    CU(p, cudaEventRecord(p->ev_comp[s], cs));
+    // copy-out
+    CU(p, cudaStreamWaitEvent(p->s_out, p->ev_comp[s], 0));
+    CU(p, cudaMemcpyAsync(Z_host, p->d_hostZ[s], (size_t)need * 4, cudaMemcpyDeviceToHost, p->s_out));
+    CU(p, cudaEventRecord(p->ev_out[s], p->s_out));
+    ++p->host_steps;
     return 0;
+}
+
+int pgcn_forward_host_wait(pgcn_plan* p)
+{
+    if (!p) return fail(nullptr, PGCN_ERR_INVALID, "null plan");
+    if (!p->s_out) return 0;
+    CU(p, cudaStreamSynchronize(p->s_out));
+    CU(p, cudaStreamSynchronize(p->host_stream));
+    return 0;
+}
+
+int pgcn_forward_host(pgcn_plan* p, const float* H_host, float* Z_host, int32_t f)
+{
+    int rc = pgcn_forward_host_async(p, H_host, Z_host, f);
+    if (rc) return rc;
+    return pgcn_forward_host_wait(p);
 }
 
 }  // extern "C"

@@ -156,6 +156,9 @@ def exchange_rows(plan, send_slab, backward=False):
 def unpack_add(plan, recv_slab, G_own):
     """G_own[send_idx[j]] += recv_slab[j] for all j, fixed order (in place). Returns G_own."""
     recv_slab = _check_feat(plan, recv_slab, plan.lp.S, "recv_slab")
+    if not G_own.is_contiguous():
+        # in/out argument: a silent .contiguous() copy would accumulate into a temporary and leave G_own unchanged
+        raise ValueError("G_own is updated in place and must be contiguous")
     G_own = _check_feat(plan, G_own, plan.lp.m, "G_own")
     with torch.cuda.device(G_own.device):
         cabi.check(cabi.load().pgcn_unpack_add(plan.handle, recv_slab.data_ptr(), G_own.data_ptr(),

@@ -153,6 +153,8 @@ def build_local_plan(A, partvec, rank, size):
     return lp
 
 
+PLAN_FORMAT_VERSION = 2      # bump when LocalPlan's layout or build_local_plan's ordering / duplicate semantics change
+
 _LP_ARRAYS = ("owned", "halo", "rowptr", "colidx", "vals", "t_rowptr", "t_colidx", "t_vals",
               "send_idx", "send_gid", "send_off", "recv_off")
 
@@ -178,13 +180,16 @@ def cached_local_plan(path_A, path_partvec, rank, size, cache_dir):
     import hashlib
     import os
     from . import graphio
-    key = hashlib.sha1(repr([os.path.abspath(path_A), os.path.getsize(path_A), int(os.path.getmtime(path_A)),
-                             os.path.abspath(path_partvec), os.path.getsize(path_partvec),
-                             int(os.path.getmtime(path_partvec)), rank, size]).encode()).hexdigest()[:16]
+    sa, sp_ = os.stat(path_A), os.stat(path_partvec)
+    key = hashlib.sha1(repr([PLAN_FORMAT_VERSION, os.path.abspath(path_A), sa.st_size, sa.st_mtime_ns,
+                             os.path.abspath(path_partvec), sp_.st_size, sp_.st_mtime_ns,
+                             rank, size]).encode()).hexdigest()[:16]
     os.makedirs(cache_dir, exist_ok=True)
     path = os.path.join(cache_dir, "plan_%s_r%dof%d.npz" % (key, rank, size))
     if os.path.exists(path):
-        return load_local_plan(path)
+        lp = load_local_plan(path)
+        if lp.k == size and lp.rank == rank:
+            return lp
     A = graphio.read_adjacency(path_A)
     pv = graphio.check_partvec(graphio.read_partvec(path_partvec, A.shape[0]), size)
     lp = build_local_plan(A, pv, rank, size)

@@ -148,3 +148,28 @@ def test_peer_transport_two_processes_one_gpu_over_cuda_ipc(tmp_path):
     for r, (pr, out) in enumerate(zip(procs, outs)):
         assert pr.returncode == 0, "rank %d failed:\n%s" % (r, out[-3000:])
         assert "rank %d ok" % r in out
+
+
+def test_more_ranks_than_the_peer_transport_takes():
+    """k = 17 > 16: plans must build and the step-by-step pieces (pack -> wire order -> SpMM, A^T g -> scatter-add)
+    must work — the NCCL transport has no rank limit; only pgcn_p2p_export refuses (fixed-size peer arrays)."""
+    import ctypes as C
+    from test_gpu_parity import forward_all, backward_all
+    n, f, k = 1700, 32, 17
+    A = graphio.synthetic_graph(n, 20000, seed=8)
+    pv = graphio.random_partvec(n, k, seed=2)
+    H = np.random.RandomState(1).uniform(-1, 1, size=(n, f)).astype(np.float32)
+    plans = [planmod.build_plan(A, pv, r, k, f, device=dev()) for r in range(k)]
+    Z = forward_all(plans, H)
+    Gd = backward_all(plans, H)
+    Z64 = orc.truth_forward(A, H); G64 = orc.truth_backward(A, H)
+    tolZ = fp32_tol(A, H, int(orc.row_degree(A).max())); tolG = fp32_tol(A.T, H, int(orc.row_degree(A.T).max()))
+    for r, p in enumerate(plans):
+        own = p.lp.owned
+        assert_close_fp32(Z[r].cpu().numpy(), Z64[own], tolZ[own], "k=17 fwd r%d" % r)
+        assert_close_fp32(Gd[r].cpu().numpy(), G64[own], tolG[own], "k=17 bwd r%d" % r)
+    blob = C.create_string_buffer(cabi.P2P_HANDLE_BYTES)
+    assert cabi.load().pgcn_p2p_export(plans[0].handle, blob) < 0          # refused, with a message
+    assert b"16" in cabi.load().pgcn_last_error(plans[0].handle)
+    for p in plans:
+        p.close()

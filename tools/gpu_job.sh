@@ -15,6 +15,17 @@ case "$job" in
     timeout 1200 ncu --set full --clock-control none --import-source on -k regex:spmm_ -s 4 -c 2 -f -o gpurun_out/prof_$tag \
         python tools/tune_spmm.py --config C2 --single "$opts" --iters 2 > gpurun_out/ncu_$tag.log 2>&1
     tail -5 gpurun_out/ncu_$tag.log ;;
+  traffic)      # DRAM bytes per launch of the default SpMM kernel -> gpurun_out/traffic_<cfg>.json (copy to profiles/)
+    cfg=${1:-C2}
+    timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+        -k regex:spmm_ring -s 4 -c 3 --csv --log-file gpurun_out/traffic_raw_$cfg.csv \
+        python tools/tune_spmm.py --config $cfg --single kernel=0 --iters 3 > gpurun_out/traffic_$cfg.log 2>&1
+    python tools/update_traffic.py gpurun_out/traffic_raw_$cfg.csv $cfg gpurun_out/traffic_$cfg.json ;;
+  configs)      # single-GPU table of the BASELINE configs (forward / transposed SpMM, checksum)
+    for c in "$@"; do
+      timeout 1200 python tools/run_config.py --config $c --iters 10 > gpurun_out/config_$c.json 2> gpurun_out/config_$c.err
+      cat gpurun_out/config_$c.json
+    done ;;
   bench)        # bench.py with the given flags
     timeout 1500 python bench.py "$@" 2> gpurun_out/bench.err | tee gpurun_out/bench_last.json ;;
   launches)     # ncu launch list of a short bench run
