@@ -128,6 +128,22 @@ __host__ __device__ constexpr size_t ring_smem_bytes(int vpl, int ns, int ng)
 // into the slots just freed. What travels from issue to consumption lives in registers (row-end mask and valid
 // mask per slot group) and in a tiny weight array; per-group overhead (mbarrier arm / wait, masks) is amortised
 // over G edges, the gather4 issue over 4 rows per instruction.
+// runtime-indexed access to a tiny register array (compare chain instead of local memory)
+template <int N>
+__device__ __forceinline__ uint32_t reg_get(const uint32_t (&a)[N], int i)
+{
+    uint32_t v = a[0];
+#pragma unroll
+    for (int k = 1; k < N; ++k) v = (i == k) ? a[k] : v;
+    return v;
+}
+template <int N>
+__device__ __forceinline__ void reg_set(uint32_t (&a)[N], int i, uint32_t v)
+{
+#pragma unroll
+    for (int k = 0; k < N; ++k) a[k] = (i == k) ? v : a[k];
+}
+
 template <int VPL, int G, int NG, int MODE, bool HALO>
 __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra, const CUtensorMap* tm0, const CUtensorMap* tm1)
 {
@@ -212,9 +228,9 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
             ++pwait;
         };
         // issue group `gi` (sub-group qs of the piece in ring slot `pslot`) into slot group sg
-        auto issue_group = [&](int gi, const int qs, const int sg) {
+        auto issue_group = [&](int gi, int qs, int sg) {
             if (gi < gA || gi > gB) {
-                vmask[sg] = 0;
+                reg_set(vmask, sg, 0u);
                 if (MODE == 1) cp_async_commit();
                 return;
             }
@@ -227,8 +243,8 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
                 valid = valid && e >= e0 && e < e1;
                 vm = __ballot_sync(0xffffffffu, valid);
             }
-            emask[sg] = __ballot_sync(0xffffffffu, valid && (cw.x & lastmask));
-            vmask[sg] = vm;
+            reg_set(emask, sg, __ballot_sync(0xffffffffu, valid && (cw.x & lastmask)));
+            reg_set(vmask, sg, vm);
             if (lane < G) w_slot[sg * G + lane] = valid ? __int_as_float(cw.y) : 0.f;
             if (MODE == 0 || MODE == 2) {
                 if (lane == 0) mbar_expect_tx(s_gbar + sg * 8, (uint32_t)__popc(vm) * RB);
@@ -292,15 +308,15 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
             for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
             ++row;
         };
-        auto consume_group = [&](const int sg) {
-            const uint32_t vm = vmask[sg];
+        auto consume_group = [&](int sg) {
+            const uint32_t vm = reg_get(vmask, sg);
             if (vm == 0) {                                               // group outside the block: nothing was issued
                 if (MODE == 1) cp_async_wait<NG - 1>();
                 return;
             }
             if (MODE != 1) { mbar_wait(s_gbar + sg * 8, (gpar >> sg) & 1); gpar ^= 1u << sg; }
             else cp_async_wait<NG - 1>();
-            const uint32_t em = emask[sg];
+            const uint32_t em = reg_get(emask, sg);
             const float4* slot = data_gen + (size_t)(sg * G) * (RB / 16);
             if (vm == FULL) {
 #pragma unroll
@@ -341,23 +357,128 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
             __syncwarp();                                                // every lane is done with these slots
         };
 
+        // ---- fast path for INTERIOR groups (all G edges valid and inside the block): no range checks, no masks ----
+        auto issue_full = [&](int qs, int sg) {
+            int2 cw = make_int2(0, 0);
+            if (lane < G) cw = idx_gen[pslot * 32 + qs * G + lane];
+            reg_set(emask, sg, __ballot_sync(0xffffffffu, cw.x & lastmask));     // lanes >= G hold zeros
+            reg_set(vmask, sg, FULL);
+            if (lane < G) w_slot[sg * G + lane] = __int_as_float(cw.y);
+            if (MODE == 1) {
+                const unsigned cj = (unsigned)(cw.x & kColMask);
+                const char* src = (cj >= usplit ? hb1 : hb0) + (size_t)cj * pitch;
+                const unsigned long long pol = (cw.x & kColdFlag) ? pol_cold : pol_hot;
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    const unsigned long long sj = __shfl_sync(0xffffffffu, (unsigned long long)src, j);
+                    const unsigned long long pj = __shfl_sync(0xffffffffu, pol, j);
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v)
+                        cp_async16(s_data + (sg * G + j) * RB + v * 512 + lane * 16,
+                                   reinterpret_cast<const char*>(sj) + v * 512 + lane * 16, pj);
+                }
+                cp_async_commit();
+                __syncwarp();
+                return;
+            }
+            if (lane == 0) mbar_expect_tx(s_gbar + sg * 8, (uint32_t)G * RB);
+            bool single = lane < G;
+            if (MODE == 2) {
+                const int qb = (lane & (G / 4 - 1)) * 4;
+                const unsigned c0 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 0);
+                const unsigned c1 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 1);
+                const unsigned c2 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 2);
+                const unsigned c3 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 3);
+                const unsigned r0 = c0 & kColMask, r1 = c1 & kColMask, r2 = c2 & kColMask, r3 = c3 & kColMask;
+                bool allhalo = false, quad_ok = true;
+                if (HALO) {
+                    const bool allown = r0 < usplit && r1 < usplit && r2 < usplit && r3 < usplit;
+                    allhalo = r0 >= usplit && r1 >= usplit && r2 >= usplit && r3 >= usplit;
+                    quad_ok = allown || allhalo;
+                    const uint32_t okmask = __ballot_sync(0xffffffffu, quad_ok) & ((1u << (G / 4)) - 1u);
+                    single = single && !((okmask >> (lane >> 2)) & 1);
+                } else {
+                    single = false;
+                }
+                if (lane < G / 4 && quad_ok) {
+                    const unsigned sub = allhalo ? usplit : 0u;
+                    const bool cold = (c0 & c1 & c2 & c3 & kColdFlag) != 0;
+                    tma_gather4(s_data + (sg * G + lane * 4) * RB, allhalo ? tm1 : tm0, (int)(blockIdx.y * (RB / 4)),
+                                (int)(r0 - sub), (int)(r1 - sub), (int)(r2 - sub), (int)(r3 - sub),
+                                s_gbar + sg * 8, cold ? pol_cold : pol_hot);
+                }
+            }
+            if (single) {
+                const unsigned cj = (unsigned)(cw.x & kColMask);
+                bulk_g2s(s_data + (sg * G + lane) * RB, (cj >= usplit ? hb1 : hb0) + (size_t)cj * pitch, RB,
+                         s_gbar + sg * 8, (cw.x & kColdFlag) ? pol_cold : pol_hot);
+            }
+        };
+        auto consume_full = [&](int sg) {
+            if (MODE != 1) { mbar_wait(s_gbar + sg * 8, (gpar >> sg) & 1); gpar ^= 1u << sg; }
+            else cp_async_wait<NG - 1>();
+            const uint32_t em = reg_get(emask, sg);
+            const float4* slot = data_gen + (size_t)(sg * G) * (RB / 16);
+#pragma unroll
+            for (int c = 0; c < G; c += 8) {
+                const float4 wa = *reinterpret_cast<const float4*>(w_slot + sg * G + c);
+                const float4 wb = *reinterpret_cast<const float4*>(w_slot + sg * G + c + 4);
+                const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                float4 r[8][VPL];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) r[j][v] = slot[(c + j) * (RB / 16) + v * 32];
+                if (((em >> c) & 0xffu) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) vfma(acc[v], w[j], r[j][v]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) vfma(acc[v], w[j], r[j][v]);
+                        if (em >> (c + j) & 1) flush_row();
+                    }
+                }
+            }
+            __syncwarp();
+        };
+
         // prologue: index pieces in flight, first piece landed, the first NG groups issued
 #pragma unroll
         for (int i = 0; i < NP; ++i) fetch_piece();
         wait_piece();
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < NG; ++i) {
             if (i > 0 && i % PG == 0) {                                  // the ring spans more than one piece
                 fetch_piece();
                 if (P0 + i / PG <= P1) wait_piece();
             }
             if (P0 + i / PG <= P1) issue_group(PG * P0 + i, i % PG, i);
-            else { vmask[i] = 0; if (MODE == 1) cp_async_commit(); }
+            else { reg_set(vmask, i, 0u); if (MODE == 1) cp_async_commit(); }
         }
         if (NG % PG == 0) fetch_piece();                                 // the last piece touched is fully issued
 
+        // The loops below are deliberately NOT unrolled over the groups of a piece: slot group and sub-group are
+        // runtime values (a handful of integer instructions per group), which keeps the whole kernel inside the
+        // instruction cache; the 8-row consume chunks inside a group are unrolled.
         for (int P = P0; P <= P1; P += U) {
-#pragma unroll
+            // interior: every group consumed AND every group issued by this body lies strictly inside the block
+            if (PG * P > gA && PG * (P + U) - 1 + NG < gB) {
+#pragma unroll 1
+                for (int idx = 0; idx < U * PG; ++idx) {
+                    const int sg = idx % NG;
+                    consume_full(sg);
+                    const int qi = (idx + NG) % PG;
+                    if (qi == 0) wait_piece();
+                    issue_full(qi, sg);
+                    if (qi == PG - 1) fetch_piece();
+                }
+                continue;
+            }
+#pragma unroll 1
             for (int idx = 0; idx < U * PG; ++idx) {
                 const int sg = idx % NG;
                 consume_group(sg);
@@ -365,7 +486,7 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
                 const int Pi = P + (idx + NG) / PG;                      // its piece
                 if (qi == 0 && Pi <= P1) wait_piece();                   // first group of a new piece
                 if (Pi <= P1) issue_group(PG * Pi + qi, qi, sg);
-                else { vmask[sg] = 0; if (MODE == 1) cp_async_commit(); }
+                else { reg_set(vmask, sg, 0u); if (MODE == 1) cp_async_commit(); }
                 if (qi == PG - 1) fetch_piece();                         // that piece is fully issued now
             }
         }
