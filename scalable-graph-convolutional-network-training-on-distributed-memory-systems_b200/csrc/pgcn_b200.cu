@@ -77,8 +77,7 @@ struct DevCsr {
     int nrows_c = 0;                // non-empty rows = rows the schedule walks
     int64_t nnz = 0;
     std::vector<int> h_rowptr;      // COMPACT row pointers (empty rows squeezed out), for scheduling
-    int2* d_cw = nullptr;           // {column | kLastFlag on the last entry of each row | kColdFlag, value bits},
-                                    // padded with zero pairs to a multiple of 32 entries (256-byte bulk-copy pieces)
+    int* d_cw = nullptr;            // entries in 272-byte pieces of 32: col[32] | val[32] | row-end mask | cold mask | pad
     int* d_rowids = nullptr;        // compact row -> output row, null when the identity
     int* d_empty = nullptr;         // output rows without entries (zero-filled when beta == 0)
     int nempty = 0;
@@ -226,21 +225,21 @@ int csr_upload(pgcn_plan* p, DevCsr& c, int nrows, const int* rowptr, const int*
 {
     c.nrows = nrows;
     c.nnz = rowptr[nrows];
-    std::vector<int2> cw((size_t)((c.nnz + 31) / 32 * 32 + 32), make_int2(0, 0));
+    const size_t npieces = (size_t)((c.nnz + 31) / 32 + 1);
+    std::vector<int> cw(npieces * kPieceInts, 0);
     for (int64_t e = 0; e < c.nnz; ++e) {
-        int cf = colidx[e];
-        if (col_refs && cold_thresh >= 0 && col_refs[colidx[e]] <= cold_thresh) cf |= kColdFlag;
-        float v = vals[e];
-        int vb;
-        memcpy(&vb, &v, 4);
-        cw[(size_t)e] = make_int2(cf, vb);
+        int* pc = cw.data() + (size_t)(e >> 5) * kPieceInts;
+        const int i = (int)(e & 31);
+        pc[i] = colidx[e];
+        memcpy(&pc[32 + i], &vals[e], 4);
+        if (col_refs && cold_thresh >= 0 && col_refs[colidx[e]] <= cold_thresh) pc[65] |= (int)(1u << i);
     }
     std::vector<int> rowids, empty;
     c.h_rowptr.clear();
     c.h_rowptr.push_back(0);
     for (int r = 0; r < nrows; ++r) {
         if (rowptr[r + 1] > rowptr[r]) {
-            cw[(size_t)rowptr[r + 1] - 1].x |= kLastFlag;
+            { const int64_t e = (int64_t)rowptr[r + 1] - 1; cw[(size_t)(e >> 5) * kPieceInts + 64] |= (int)(1u << (e & 31)); }
             c.h_rowptr.push_back(rowptr[r + 1]);
             rowids.push_back(ext_rowmap ? (*ext_rowmap)[r] : r);
         } else if (!ext_rowmap) {
@@ -510,7 +509,7 @@ int launch_spmm(pgcn_plan* p, DevCsr& c, const float* H0, const float* H1, int s
     }
     SpmmArgs a;
     a.blocks = sc.d_blocks; a.nblocks = sc.nblocks;
-    a.cw = c.d_cw;
+    a.pieces = c.d_cw;
     a.H0 = H0; a.H1 = H1; a.split = split;
     a.Z0 = Z0; a.Z1 = Z1; a.zsplit = zsplit;
     a.rowids = c.d_rowids;

@@ -34,6 +34,14 @@ namespace pgcn {
 // Bit 30 marks a COLD column (few references): its H row is loaded with an L2 evict_first policy
 // while the hot rows (hubs, the part of H that fits in L2) are loaded evict_last, so streaming
 // traffic does not push the re-used rows out of the 126 MB L2.
+// Device layout of a CSR's entries: consecutive PIECES of 32 entries, one 272-byte record each (one TMA bulk copy):
+//   int   col[32]    plain column indices (no flag bits: they go straight into TMA gather4 coordinates)
+//   float val[32]
+//   uint  emask      bit i: entry i is the LAST of its row        uint cmask   bit i: entry i's column is COLD
+//   uint  pad[2]
+// Entry e lives in piece e >> 5 at index e & 31. The register kernel rebuilds {col | flags, val} pairs as it loads.
+constexpr int kPieceInts = 68;
+constexpr int kPieceBytes = kPieceInts * 4;
 constexpr int kLastFlag = (int)0x80000000;
 constexpr int kColdFlag = 0x40000000;
 constexpr int kColMask = 0x3fffffff;
@@ -45,8 +53,7 @@ constexpr int kColMask = 0x3fffffff;
 struct SpmmArgs {
     const int4* blocks;      // {first row (compact id), nrows | -(slot+1), e_begin, e_end}
     int nblocks;
-    const int2* cw;          // per stored entry {column | flags, value bits}; kLastFlag on the last entry of
-                             // each (non-empty) row; padded to a multiple of 32 entries (bulk-copy pieces)
+    const int* pieces;       // the matrix entries in PIECES of 32 (kPieceInts ints = 272 bytes each, see below)
     const float* H0;         // columns [0, split)
     const float* H1;         // columns [split, ...)   (halo slab), may be null when unused
     int split;
@@ -114,7 +121,16 @@ __device__ __forceinline__ float ld_feat_hint(const float* p, unsigned long long
     return r;
 }
 // column indices / values: touched once -> streaming, do not displace H rows.
-__device__ __forceinline__ int2 ld_stream(const int2* p) { return __ldcs(p); }
+// entry e of the piece array as the {column | kLastFlag | kColdFlag, value bits} pair the register kernel walks
+__device__ __forceinline__ int2 ld_entry(const int* pieces, int e)
+{
+    const int* pc = pieces + (size_t)(e >> 5) * kPieceInts;
+    const int i = e & 31;
+    const int col = __ldcs(pc + i);
+    const int val = __ldcs(pc + 32 + i);
+    const int2 m = __ldcs(reinterpret_cast<const int2*>(pc + 64));
+    return make_int2(col | (((unsigned)m.x >> i) & 1u ? kLastFlag : 0) | (((unsigned)m.y >> i) & 1u ? kColdFlag : 0), val);
+}
 // outputs: written once -> streaming stores.
 __device__ __forceinline__ void st_out(float4* p, const float4& v) { __stcs(p, v); }
 __device__ __forceinline__ void st_out(float* p, const float& v) { __stcs(p, v); }
@@ -236,11 +252,11 @@ spmm_rowblock_kernel(const SpmmArgs a)
     int buf = 0;
     {
         int2 cw = make_int2(0, 0);
-        if (e + gl < e_end) cw = ld_stream(a.cw + e + gl);
+        if (e + gl < e_end) cw = ld_entry(a.pieces, e + gl);
         s_cw[0][threadIdx.x] = cw;
     }
     int2 cw_next = make_int2(0, 0);
-    if (e + LPE + gl < e_end) cw_next = ld_stream(a.cw + e + LPE + gl);
+    if (e + LPE + gl < e_end) cw_next = ld_entry(a.pieces, e + LPE + gl);
     __syncwarp(gmask);
 
     while (e < e_end) {
@@ -281,7 +297,7 @@ spmm_rowblock_kernel(const SpmmArgs a)
         buf ^= 1;
         s_cw[buf][threadIdx.x] = cw_next;
         cw_next = make_int2(0, 0);
-        if (e + LPE + gl < e_end) cw_next = ld_stream(a.cw + e + LPE + gl);
+        if (e + LPE + gl < e_end) cw_next = ld_entry(a.pieces, e + LPE + gl);
         __syncwarp(gmask);
     }
 

@@ -95,7 +95,7 @@ __device__ __noinline__ void ring_store_row(float4 a0, float4 a1, const int* row
 }
 
 constexpr int kRingWarps = 2;        // warps per CTA (each fully independent: CTA size only sets the smem granule)
-constexpr int kRingPieces = 4;       // index pieces (32 entries = 256 B each) per warp
+constexpr int kRingPieces = 4;       // index pieces (32 entries, kPieceBytes each) resident per warp
 
 struct RingArgs {
     unsigned int* counter;   // null: block = blockIdx.x * kRingWarps + warp; else dynamic (persistent CTAs)
@@ -103,31 +103,16 @@ struct RingArgs {
     int nhub;
 };
 
-// per warp: NS row slots | NP index pieces | NS weights | NG + NP mbarriers
+// per warp: NS row slots | NP index pieces | NG + NP mbarriers
 __host__ __device__ constexpr size_t ring_warp_bytes(int vpl, int ns, int ng)
 {
-    return ((size_t)ns * vpl * 512 + (size_t)kRingPieces * 256 + (size_t)ns * 4 +
-            (size_t)(ng + kRingPieces) * 8 + 127) / 128 * 128;
+    return ((size_t)ns * vpl * 512 + (size_t)kRingPieces * kPieceBytes + (size_t)(ng + kRingPieces) * 8 + 127) / 128 * 128;
 }
 __host__ __device__ constexpr size_t ring_smem_bytes(int vpl, int ns, int ng)
 {
     return ring_warp_bytes(vpl, ns, ng) * kRingWarps + 128;
 }
 
-// VPL : 128-float vector groups per row (tile of f).
-// G   : edges per completion group (8, 16 or 32); NG: groups in the ring (2 or 4); the warp owns NS = G * NG row slots.
-// MODE: 0 = 1-D TMA bulk copies (UBLKCP, one per row), 1 = per-lane 16-byte cp.async (LDGSTS + wait_group),
-//       2 = 2-D tensor-map TMA in tile::gather4 mode (UTMALDG.2D.GATHER4, FOUR rows per instruction; quads that mix
-//           own and halo columns, or groups cut by a block boundary, fall back to the 1-D copies of MODE 0).
-// HALO: columns >= split live in a second matrix (the halo slab).
-//
-// The edge stream is walked in GLOBALLY ALIGNED units: a piece = entries [32 P, 32 P + 32) of the pair array (one
-// 256-byte bulk copy), a group = entries [G g, G g + G) (one completion unit of the row ring, slot group g % NG).
-// A row block [e0, e1) starts and ends anywhere; entries of its first / last group outside the block are masked.
-// Because everything is aligned, the loop body has STATIC slot numbers: consume group g, then issue group g + NG
-// into the slots just freed. What travels from issue to consumption lives in registers (row-end mask and valid
-// mask per slot group) and in a tiny weight array; per-group overhead (mbarrier arm / wait, masks) is amortised
-// over G edges, the gather4 issue over 4 rows per instruction.
 // runtime-indexed access to a tiny register array (compare chain instead of local memory)
 template <int N>
 __device__ __forceinline__ uint32_t reg_get(const uint32_t (&a)[N], int i)
@@ -144,6 +129,23 @@ __device__ __forceinline__ void reg_set(uint32_t (&a)[N], int i, uint32_t v)
     for (int k = 0; k < N; ++k) a[k] = (i == k) ? v : a[k];
 }
 
+// VPL : 128-float vector groups per row (tile of f).
+// G   : edges per completion group (8, 16 or 32); NG: groups in the ring (2 or 4); the warp owns NS = G * NG row slots.
+// MODE: 0 = 1-D TMA bulk copies (UBLKCP, one per row), 1 = per-lane 16-byte cp.async (LDGSTS + wait_group),
+//       2 = 2-D tensor-map TMA in tile::gather4 mode (UTMALDG.2D.GATHER4, FOUR rows per instruction; quads that mix
+//           own and halo columns, or groups cut by a block boundary, fall back to the 1-D copies of MODE 0).
+// HALO: columns >= split live in a second matrix (the halo slab).
+//
+// The entries are walked in GLOBALLY ALIGNED units: a piece = entries [32 P, 32 P + 32) (one 272-byte record =
+// one bulk copy: 32 plain column indices, 32 values, a row-end bit mask and a cold-column bit mask), a group =
+// entries [G g, G g + G) (one completion unit of the row ring, slot group g % NG). A row block [e0, e1) starts and
+// ends anywhere; entries of its first / last group outside the block are masked. The steady state per group is:
+//   issue   : one broadcast LDS.64 (masks), lanes 0..G/4-1 read their four column indices with one LDS.128 and
+//             fire one gather4 each; lane 0 arms the group's mbarrier with G x row bytes;
+//   consume : mbarrier wait, 8 x LDS.128 rows + 2 x LDS.128 values (straight from the resident piece), 32 FFMA per
+//             8 edges; a row-end test per edge only in groups whose row-end mask is non-zero.
+// Pieces stay resident until their last group has been CONSUMED (the values are read at consumption time), so
+// nothing is copied between issue and consumption except the row-end mask, which travels in a register.
 template <int VPL, int G, int NG, int MODE, bool HALO>
 __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra, const CUtensorMap* tm0, const CUtensorMap* tm1)
 {
@@ -153,17 +155,17 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
     constexpr uint32_t RB = VPL * 512;                                   // bytes of one row tile
     constexpr uint32_t FULL = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
     static_assert((G == 8 || G == 16 || G == 32) && (NG == 2 || NG == 4), "unsupported ring shape");
-    static_assert((U * PG) % NG == 0, "slot groups must be static in the loop body");
+    static_assert((U * PG) % NG == 0, "slot groups must repeat with the loop body");
+    static_assert(NP * 32 >= NS + 64, "pieces must stay resident from prefetch to consumption");
     extern __shared__ __align__(128) unsigned char ring_smem[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wbase = ring_smem + (size_t)warp * ring_warp_bytes(VPL, NS, NG);
     const uint32_t s_data = smem_u32(wbase);                             // NS slots of RB bytes
-    const uint32_t s_idx = s_data + NS * RB;                             // NP pieces of 32 int2
-    const uint32_t s_gbar = s_idx + NP * 256 + NS * 4;                   // NG group barriers
+    const uint32_t s_idx = s_data + NS * RB;                             // NP pieces
+    const uint32_t s_gbar = s_idx + NP * kPieceBytes;                    // NG group barriers
     const uint32_t s_pbar = s_gbar + NG * 8;                             // NP piece barriers
-    const int2* idx_gen = reinterpret_cast<const int2*>(wbase + (size_t)NS * RB);
-    float* w_slot = reinterpret_cast<float*>(wbase + (size_t)NS * RB + NP * 256);   // weight of the edge in each slot
+    const int* idx_gen = reinterpret_cast<const int*>(wbase + (size_t)NS * RB);
     const float4* data_gen = reinterpret_cast<const float4*>(wbase) + lane;
 
     if (lane == 0) {
@@ -185,7 +187,8 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
     unsigned int* counter = ra.counter ? ra.counter + blockIdx.y : nullptr;
 
     uint32_t gpar = 0;                   // phase parity of each group barrier (bit sg)
-    uint32_t pfetch = 0, pwait = 0;      // pieces fetched / waited for by this warp so far (FIFO through NP slots)
+    // pieces move through the NP slots as a FIFO: fetched -> landed (issue side) -> consumed
+    uint32_t pfetch = 0, pwait = 0, pcons = 0;
 
     float4 acc[VPL];
 #pragma unroll
@@ -200,7 +203,6 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
     while (blk < a.nblocks) {
         const int4 b = __ldg(a.blocks + blk);
         const bool seg = b.y < 0;
-        const int lastmask = seg ? 0 : kLastFlag;
         const int e0 = b.z, e1 = b.w;
         int row = b.x;
         const int gA = e0 / G, gB = (e1 - 1) / G;                        // first / last (aligned) group
@@ -209,98 +211,30 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
 #pragma unroll
         for (int i = 0; i < NG; ++i) vmask[i] = emask[i] = 0;
         int pnext = P0;                                                  // next piece to fetch
-        uint32_t pslot = pwait % NP;                                     // ring slot of the piece being issued from
+        const int* pi = idx_gen;                                         // piece being issued from
+        const int* pc = idx_gen + (pcons % NP) * kPieceInts;             // piece being consumed from
 
         auto fetch_piece = [&]() {
             if (pnext <= P1) {
                 if (lane == 0) {
                     const uint32_t q = pfetch % NP;
-                    mbar_expect_tx(s_pbar + q * 8, 256);
-                    bulk_g2s(s_idx + q * 256, a.cw + (size_t)pnext * 32, 256, s_pbar + q * 8, pol_cold);
+                    mbar_expect_tx(s_pbar + q * 8, kPieceBytes);
+                    bulk_g2s(s_idx + q * kPieceBytes, a.pieces + (size_t)pnext * kPieceInts, kPieceBytes, s_pbar + q * 8, pol_cold);
                 }
                 ++pfetch;
                 ++pnext;
             }
         };
         auto wait_piece = [&]() {                                        // the next piece in FIFO order has landed
-            pslot = pwait % NP;
-            mbar_wait(s_pbar + pslot * 8, (pwait / NP) & 1);
+            const uint32_t q = pwait % NP;
+            mbar_wait(s_pbar + q * 8, (pwait / NP) & 1);
+            pi = idx_gen + q * kPieceInts;
             ++pwait;
         };
-        // issue group `gi` (sub-group qs of the piece in ring slot `pslot`) into slot group sg
-        auto issue_group = [&](int gi, int qs, int sg) {
-            if (gi < gA || gi > gB) {
-                reg_set(vmask, sg, 0u);
-                if (MODE == 1) cp_async_commit();
-                return;
-            }
-            int2 cw = make_int2(0, 0);
-            if (lane < G) cw = idx_gen[pslot * 32 + qs * G + lane];
-            bool valid = lane < G;
-            uint32_t vm = FULL;
-            if (gi == gA || gi == gB) {                                  // first / last group of the block: mask
-                const int e = gi * G + lane;
-                valid = valid && e >= e0 && e < e1;
-                vm = __ballot_sync(0xffffffffu, valid);
-            }
-            reg_set(emask, sg, __ballot_sync(0xffffffffu, valid && (cw.x & lastmask)));
-            reg_set(vmask, sg, vm);
-            if (lane < G) w_slot[sg * G + lane] = valid ? __int_as_float(cw.y) : 0.f;
-            if (MODE == 0 || MODE == 2) {
-                if (lane == 0) mbar_expect_tx(s_gbar + sg * 8, (uint32_t)__popc(vm) * RB);
-                bool single = valid;                                     // this lane copies its own row (1-D bulk)
-                if (MODE == 2 && vm == FULL) {
-                    // lanes 0 .. G/4-1 each look at the four columns of one quad (entries 4 q .. 4 q + 3 of the group)
-                    const int qb = (lane & (G / 4 - 1)) * 4;
-                    const unsigned c0 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 0);
-                    const unsigned c1 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 1);
-                    const unsigned c2 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 2);
-                    const unsigned c3 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 3);
-                    const unsigned r0 = c0 & kColMask, r1 = c1 & kColMask, r2 = c2 & kColMask, r3 = c3 & kColMask;
-                    bool allhalo = false, quad_ok = true;
-                    if (HALO) {
-                        const bool allown = r0 < usplit && r1 < usplit && r2 < usplit && r3 < usplit;
-                        allhalo = r0 >= usplit && r1 >= usplit && r2 >= usplit && r3 >= usplit;
-                        quad_ok = allown || allhalo;
-                        const uint32_t okmask = __ballot_sync(0xffffffffu, quad_ok) & ((1u << (G / 4)) - 1u);
-                        single = valid && !((okmask >> (lane >> 2)) & 1);
-                    } else {
-                        single = false;
-                    }
-                    __syncwarp();
-                    if (lane < G / 4 && quad_ok) {
-                        const unsigned sub = allhalo ? usplit : 0u;
-                        const bool cold = (c0 & c1 & c2 & c3 & kColdFlag) != 0;
-                        tma_gather4(s_data + (sg * G + lane * 4) * RB, allhalo ? tm1 : tm0, (int)(blockIdx.y * (RB / 4)),
-                                    (int)(r0 - sub), (int)(r1 - sub), (int)(r2 - sub), (int)(r3 - sub),
-                                    s_gbar + sg * 8, cold ? pol_cold : pol_hot);
-                    }
-                } else {
-                    __syncwarp();
-                }
-                if (single) {
-                    const unsigned cj = (unsigned)(cw.x & kColMask);
-                    bulk_g2s(s_data + (sg * G + lane) * RB, (cj >= usplit ? hb1 : hb0) + (size_t)cj * pitch, RB,
-                             s_gbar + sg * 8, (cw.x & kColdFlag) ? pol_cold : pol_hot);
-                }
-            } else {
-                const unsigned cj = (unsigned)(cw.x & kColMask);
-                const char* src = (cj >= usplit ? hb1 : hb0) + (size_t)cj * pitch;
-                const unsigned long long pol = (cw.x & kColdFlag) ? pol_cold : pol_hot;
-#pragma unroll
-                for (int j = 0; j < G; ++j) {
-                    const unsigned long long sj = __shfl_sync(0xffffffffu, (unsigned long long)src, j);
-                    const unsigned long long pj = __shfl_sync(0xffffffffu, pol, j);
-                    if (vm >> j & 1) {
-#pragma unroll
-                        for (int v = 0; v < VPL; ++v)
-                            cp_async16(s_data + (sg * G + j) * RB + v * 512 + lane * 16,
-                                       reinterpret_cast<const char*>(sj) + v * 512 + lane * 16, pj);
-                    }
-                }
-                cp_async_commit();
-                __syncwarp();
-            }
+        auto piece_consumed = [&]() {                                    // the consumer leaves its piece: slot is free
+            ++pcons;
+            pc = idx_gen + (pcons % NP) * kPieceInts;
+            fetch_piece();
         };
         auto flush_row = [&]() {
             ring_store_row<VPL>(acc[0], acc[VPL - 1], a.rowids, row, a.Z0, a.Z1, a.zsplit, pitch, toff + lane * 16, a.beta);
@@ -308,8 +242,64 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
             for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
             ++row;
         };
-        auto consume_group = [&](int sg) {
-            const uint32_t vm = reg_get(vmask, sg);
+        // issue the group at sub-position qs of piece `pi` into slot group sg; vm = valid entries (FULL inside the block)
+        auto issue = [&](int qs, int sg, uint32_t vm) {
+            const uint2 m = *reinterpret_cast<const uint2*>(pi + 64);    // {row-end mask, cold mask} of the piece
+            const uint32_t em = seg ? 0u : ((m.x >> (qs * G)) & vm);
+            const uint32_t cm = (m.y >> (qs * G)) & FULL;
+            reg_set(emask, sg, em);
+            reg_set(vmask, sg, vm);
+            const int* cols = pi + qs * G;
+            if (MODE == 1) {
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    if (vm >> j & 1) {
+                        const unsigned cj = (unsigned)cols[j];
+                        const char* src = (cj >= usplit ? hb1 : hb0) + (size_t)cj * pitch + lane * 16;
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v)
+                            cp_async16(s_data + (sg * G + j) * RB + v * 512 + lane * 16, src + v * 512,
+                                       (cm >> j & 1) ? pol_cold : pol_hot);
+                    }
+                }
+                cp_async_commit();
+                return;
+            }
+            if (lane == 0) mbar_expect_tx(s_gbar + sg * 8, (uint32_t)__popc(vm) * RB);
+            uint32_t single = vm;                                        // entries copied one row at a time (1-D bulk)
+            if (MODE == 2 && vm == FULL) {
+                bool fire = lane < G / 4;
+                int4 q4 = make_int4(0, 0, 0, 0);
+                if (fire) q4 = *reinterpret_cast<const int4*>(cols + lane * 4);
+                bool allhalo = false;
+                if (HALO) {
+                    const unsigned r0 = (unsigned)q4.x, r1 = (unsigned)q4.y, r2 = (unsigned)q4.z, r3 = (unsigned)q4.w;
+                    const bool allown = r0 < usplit && r1 < usplit && r2 < usplit && r3 < usplit;
+                    allhalo = r0 >= usplit && r1 >= usplit && r2 >= usplit && r3 >= usplit;
+                    fire = fire && (allown || allhalo);
+                    const uint32_t okq = __ballot_sync(0xffffffffu, fire);      // bit q: quad q goes out as one gather4
+                    single = 0;
+#pragma unroll
+                    for (int q = 0; q < G / 4; ++q) single |= (okq >> q & 1) ? 0u : (0xfu << (4 * q));
+                } else {
+                    single = 0;
+                }
+                if (fire) {
+                    const int sub = allhalo ? (int)usplit : 0;
+                    const bool cold = ((cm >> (lane * 4)) & 0xfu) == 0xfu;
+                    tma_gather4(s_data + (sg * G + lane * 4) * RB, allhalo ? tm1 : tm0, (int)(blockIdx.y * (RB / 4)),
+                                q4.x - sub, q4.y - sub, q4.z - sub, q4.w - sub, s_gbar + sg * 8, cold ? pol_cold : pol_hot);
+                }
+            }
+            if (lane < G && (single >> lane & 1)) {
+                const unsigned cj = (unsigned)cols[lane];
+                bulk_g2s(s_data + (sg * G + lane) * RB, (cj >= usplit ? hb1 : hb0) + (size_t)cj * pitch, RB,
+                         s_gbar + sg * 8, (cm >> lane & 1) ? pol_cold : pol_hot);
+            }
+        };
+        // consume slot group sg = the group at sub-position qs of piece `pc`
+        auto consume = [&](int qs, int sg, bool interior) {
+            const uint32_t vm = interior ? FULL : reg_get(vmask, sg);
             if (vm == 0) {                                               // group outside the block: nothing was issued
                 if (MODE == 1) cp_async_wait<NG - 1>();
                 return;
@@ -318,11 +308,12 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
             else cp_async_wait<NG - 1>();
             const uint32_t em = reg_get(emask, sg);
             const float4* slot = data_gen + (size_t)(sg * G) * (RB / 16);
+            const float* wv = reinterpret_cast<const float*>(pc) + 32 + qs * G;
             if (vm == FULL) {
 #pragma unroll
                 for (int c = 0; c < G; c += 8) {                         // 8 rows at a time: 8 x LDS.128 in flight
-                    const float4 wa = *reinterpret_cast<const float4*>(w_slot + sg * G + c);
-                    const float4 wb = *reinterpret_cast<const float4*>(w_slot + sg * G + c + 4);
+                    const float4 wa = *reinterpret_cast<const float4*>(wv + c);
+                    const float4 wb = *reinterpret_cast<const float4*>(wv + c + 4);
                     const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
                     float4 r[8][VPL];
 #pragma unroll
@@ -347,7 +338,7 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
 #pragma unroll 1
                 for (int j = 0; j < G; ++j) {
                     if (vm >> j & 1) {
-                        const float wj = w_slot[sg * G + j];
+                        const float wj = wv[j];
 #pragma unroll
                         for (int v = 0; v < VPL; ++v) vfma(acc[v], wj, slot[j * (RB / 16) + v * 32]);
                         if (em >> j & 1) flush_row();
@@ -356,94 +347,18 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
             }
             __syncwarp();                                                // every lane is done with these slots
         };
-
-        // ---- fast path for INTERIOR groups (all G edges valid and inside the block): no range checks, no masks ----
-        auto issue_full = [&](int qs, int sg) {
-            int2 cw = make_int2(0, 0);
-            if (lane < G) cw = idx_gen[pslot * 32 + qs * G + lane];
-            reg_set(emask, sg, __ballot_sync(0xffffffffu, cw.x & lastmask));     // lanes >= G hold zeros
-            reg_set(vmask, sg, FULL);
-            if (lane < G) w_slot[sg * G + lane] = __int_as_float(cw.y);
-            if (MODE == 1) {
-                const unsigned cj = (unsigned)(cw.x & kColMask);
-                const char* src = (cj >= usplit ? hb1 : hb0) + (size_t)cj * pitch;
-                const unsigned long long pol = (cw.x & kColdFlag) ? pol_cold : pol_hot;
-#pragma unroll
-                for (int j = 0; j < G; ++j) {
-                    const unsigned long long sj = __shfl_sync(0xffffffffu, (unsigned long long)src, j);
-                    const unsigned long long pj = __shfl_sync(0xffffffffu, pol, j);
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v)
-                        cp_async16(s_data + (sg * G + j) * RB + v * 512 + lane * 16,
-                                   reinterpret_cast<const char*>(sj) + v * 512 + lane * 16, pj);
-                }
-                cp_async_commit();
-                __syncwarp();
-                return;
-            }
-            if (lane == 0) mbar_expect_tx(s_gbar + sg * 8, (uint32_t)G * RB);
-            bool single = lane < G;
-            if (MODE == 2) {
-                const int qb = (lane & (G / 4 - 1)) * 4;
-                const unsigned c0 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 0);
-                const unsigned c1 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 1);
-                const unsigned c2 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 2);
-                const unsigned c3 = (unsigned)__shfl_sync(0xffffffffu, cw.x, qb + 3);
-                const unsigned r0 = c0 & kColMask, r1 = c1 & kColMask, r2 = c2 & kColMask, r3 = c3 & kColMask;
-                bool allhalo = false, quad_ok = true;
-                if (HALO) {
-                    const bool allown = r0 < usplit && r1 < usplit && r2 < usplit && r3 < usplit;
-                    allhalo = r0 >= usplit && r1 >= usplit && r2 >= usplit && r3 >= usplit;
-                    quad_ok = allown || allhalo;
-                    const uint32_t okmask = __ballot_sync(0xffffffffu, quad_ok) & ((1u << (G / 4)) - 1u);
-                    single = single && !((okmask >> (lane >> 2)) & 1);
-                } else {
-                    single = false;
-                }
-                if (lane < G / 4 && quad_ok) {
-                    const unsigned sub = allhalo ? usplit : 0u;
-                    const bool cold = (c0 & c1 & c2 & c3 & kColdFlag) != 0;
-                    tma_gather4(s_data + (sg * G + lane * 4) * RB, allhalo ? tm1 : tm0, (int)(blockIdx.y * (RB / 4)),
-                                (int)(r0 - sub), (int)(r1 - sub), (int)(r2 - sub), (int)(r3 - sub),
-                                s_gbar + sg * 8, cold ? pol_cold : pol_hot);
-                }
-            }
-            if (single) {
-                const unsigned cj = (unsigned)(cw.x & kColMask);
-                bulk_g2s(s_data + (sg * G + lane) * RB, (cj >= usplit ? hb1 : hb0) + (size_t)cj * pitch, RB,
-                         s_gbar + sg * 8, (cw.x & kColdFlag) ? pol_cold : pol_hot);
-            }
+        // valid-entry mask of aligned group gi with respect to the block [e0, e1)
+        auto group_mask = [&](int gi) -> uint32_t {
+            if (gi < gA || gi > gB) return 0u;
+            uint32_t vm = FULL;
+            if (gi == gA) vm &= FULL << (e0 - gA * G);
+            if (gi == gB) vm &= FULL >> (G - 1 - ((e1 - 1) - gB * G));
+            return vm;
         };
-        auto consume_full = [&](int sg) {
-            if (MODE != 1) { mbar_wait(s_gbar + sg * 8, (gpar >> sg) & 1); gpar ^= 1u << sg; }
-            else cp_async_wait<NG - 1>();
-            const uint32_t em = reg_get(emask, sg);
-            const float4* slot = data_gen + (size_t)(sg * G) * (RB / 16);
-#pragma unroll
-            for (int c = 0; c < G; c += 8) {
-                const float4 wa = *reinterpret_cast<const float4*>(w_slot + sg * G + c);
-                const float4 wb = *reinterpret_cast<const float4*>(w_slot + sg * G + c + 4);
-                const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-                float4 r[8][VPL];
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) r[j][v] = slot[(c + j) * (RB / 16) + v * 32];
-                if (((em >> c) & 0xffu) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-#pragma unroll
-                        for (int v = 0; v < VPL; ++v) vfma(acc[v], w[j], r[j][v]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-#pragma unroll
-                        for (int v = 0; v < VPL; ++v) vfma(acc[v], w[j], r[j][v]);
-                        if (em >> (c + j) & 1) flush_row();
-                    }
-                }
-            }
-            __syncwarp();
+        auto issue_checked = [&](int gi, int qs, int sg) {
+            const uint32_t vm = group_mask(gi);
+            if (vm == 0) { reg_set(vmask, sg, 0u); if (MODE == 1) cp_async_commit(); return; }
+            issue(qs, sg, vm);
         };
 
         // prologue: index pieces in flight, first piece landed, the first NG groups issued
@@ -452,44 +367,37 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
         wait_piece();
 #pragma unroll 1
         for (int i = 0; i < NG; ++i) {
-            if (i > 0 && i % PG == 0) {                                  // the ring spans more than one piece
-                fetch_piece();
-                if (P0 + i / PG <= P1) wait_piece();
-            }
-            if (P0 + i / PG <= P1) issue_group(PG * P0 + i, i % PG, i);
+            if (i > 0 && i % PG == 0 && P0 + i / PG <= P1) wait_piece();     // the ring spans more than one piece
+            if (P0 + i / PG <= P1) issue_checked(PG * P0 + i, i % PG, i);
             else { reg_set(vmask, i, 0u); if (MODE == 1) cp_async_commit(); }
         }
-        if (NG % PG == 0) fetch_piece();                                 // the last piece touched is fully issued
 
         // The loops below are deliberately NOT unrolled over the groups of a piece: slot group and sub-group are
         // runtime values (a handful of integer instructions per group), which keeps the whole kernel inside the
         // instruction cache; the 8-row consume chunks inside a group are unrolled.
         for (int P = P0; P <= P1; P += U) {
             // interior: every group consumed AND every group issued by this body lies strictly inside the block
-            if (PG * P > gA && PG * (P + U) - 1 + NG < gB) {
-#pragma unroll 1
-                for (int idx = 0; idx < U * PG; ++idx) {
-                    const int sg = idx % NG;
-                    consume_full(sg);
-                    const int qi = (idx + NG) % PG;
-                    if (qi == 0) wait_piece();
-                    issue_full(qi, sg);
-                    if (qi == PG - 1) fetch_piece();
-                }
-                continue;
-            }
+            const bool interior = PG * P > gA && PG * (P + U) - 1 + NG < gB;
 #pragma unroll 1
             for (int idx = 0; idx < U * PG; ++idx) {
                 const int sg = idx % NG;
-                consume_group(sg);
-                const int qi = (idx + NG) % PG;                          // sub-group of the group NG ahead
+                const int qc = idx % PG;                                 // sub-position of the consumed group
+                consume(qc, sg, interior);
+                if (qc == PG - 1) piece_consumed();
+                const int qi = (idx + NG) % PG;                          // sub-position of the group NG ahead
                 const int Pi = P + (idx + NG) / PG;                      // its piece
-                if (qi == 0 && Pi <= P1) wait_piece();                   // first group of a new piece
-                if (Pi <= P1) issue_group(PG * Pi + qi, qi, sg);
-                else { reg_set(vmask, sg, 0u); if (MODE == 1) cp_async_commit(); }
-                if (qi == PG - 1) fetch_piece();                         // that piece is fully issued now
+                if (interior) {
+                    if (qi == 0) wait_piece();
+                    issue(qi, sg, FULL);
+                } else {
+                    if (qi == 0 && Pi <= P1) wait_piece();               // first group of a new piece
+                    if (Pi <= P1) issue_checked(PG * Pi + qi, qi, sg);
+                    else { reg_set(vmask, sg, 0u); if (MODE == 1) cp_async_commit(); }
+                }
             }
         }
+        // pieces P1+1 .. (rounded up to the body) were never fetched, but the body counted them as consumed
+        pcons = pwait;
 
         if (seg) {
             char* pb = reinterpret_cast<char*>(a.partial) + (size_t)(unsigned)(-b.y - 1) * pitch + toff;
