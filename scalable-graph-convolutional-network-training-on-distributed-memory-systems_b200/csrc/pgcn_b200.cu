@@ -471,6 +471,34 @@ ring_g4_fn pick_ring_g4(int vpl, int shape, bool halo)
     return halo ? pick_ring_g4_t<1, true>(shape) : pick_ring_g4_t<1, false>(shape);
 }
 
+// CUDA loads kernels lazily, at their first launch, and that load synchronises with the device. A rank whose
+// stream already holds a spinning p2p_wait_kernel must therefore never launch a not-yet-loaded kernel behind it
+// when the ranks it waits for live in the SAME process (single-process multi-rank use: tests, smoke) — their put
+// kernels would never be enqueued. Touching every kernel once, when the peer transport is set up, removes the hazard.
+template <class F>
+void touch_kernel(F fn) { cudaFuncAttributes fa; if (cudaFuncGetAttributes(&fa, (const void*)fn) != cudaSuccess) cudaGetLastError(); }
+
+void preload_kernels()
+{
+    static bool done = false;
+    if (done) return;
+    done = true;
+    for (int halo = 0; halo < 2; ++halo)
+        for (int lpe = 4; lpe <= 32; lpe *= 2)
+            for (int vpl = 1; vpl <= 4; vpl *= 2) { touch_kernel(pick_lpe<4>(lpe, vpl, halo != 0)); touch_kernel(pick_lpe<1>(lpe, vpl, halo != 0)); }
+    for (int vpl = 1; vpl <= 2; ++vpl)
+        for (int halo = 0; halo < 2; ++halo) {
+            for (int shape = 0; shape < 4; ++shape) touch_kernel(pick_ring_g4(vpl, shape, halo != 0));
+            for (int shape = 0; shape < 2; ++shape) touch_kernel(pick_ring(vpl, shape, 0, halo != 0));
+            touch_kernel(pick_ring(vpl, 0, 1, halo != 0));
+        }
+    touch_kernel(zero_rows_kernel<4>); touch_kernel(zero_rows_kernel<1>);
+    touch_kernel(spmm_fixup_kernel<4>); touch_kernel(spmm_fixup_kernel<1>);
+    touch_kernel(pack_rows_kernel<4>); touch_kernel(pack_rows_kernel<1>);
+    touch_kernel(unpack_add_kernel<4>); touch_kernel(unpack_add_kernel<1>);
+    touch_kernel(put_rows_kernel<4>); touch_kernel(p2p_wait_kernel);
+}
+
 bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
 // Which SpMM kernel serves width f with these operands: the shared-memory ring (TMA bulk copies) needs whole
@@ -1150,6 +1178,7 @@ int pgcn_p2p_import(pgcn_plan* p, const void* handles_k)
         }
         CU(p, cudaIpcOpenMemHandle(&p->peer_arena[q], b.ipc, cudaIpcMemLazyEnablePeerAccess));
     }
+    preload_kernels();
     p->p2p = p->opt_p2p != 0;
     return 0;
 }

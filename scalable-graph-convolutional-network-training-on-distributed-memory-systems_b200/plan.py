@@ -285,7 +285,7 @@ class PgcnPlan:
         return int(self._lib.pgcn_launch_count(self.handle))
 
     # -- communicator --------------------------------------------------------------------------
-    def init_comm(self, group=None, transport="auto"):
+    def init_comm(self, group=None, transport="auto", nccl_fallback=True):
         """Collective. transport: "nccl" (grouped ncclSend/ncclRecv), "p2p" (peer-memory stores over
         NVLink, single box), or "auto" (p2p when every rank can export/import, else nccl)."""
         import torch
@@ -324,9 +324,9 @@ class PgcnPlan:
         # the NCCL communicator is always created: it is the transport of the step-by-step entry points
         # (pgcn_exchange) and the fallback of the fused ones for widths the peer-store kernels do not take
         # (f % 4 != 0)
-        if used == "p2p" and transport == "p2p":
-            # explicitly peer-memory only (e.g. several ranks sharing one device, where NCCL cannot be set up):
-            # widths the peer-store kernels do not take (f % 4 != 0) then have no transport and raise
+        if used == "p2p" and not nccl_fallback:
+            # peer-memory only (e.g. several ranks sharing one device, where NCCL cannot be set up): widths the
+            # peer-store kernels do not take (f % 4 != 0) then have no transport and raise
             return used
         ident = torch.zeros(cabi.NCCL_ID_BYTES, dtype=torch.uint8)
         if self.lp.rank == 0:

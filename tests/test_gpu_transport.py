@@ -106,7 +106,7 @@ g = Golden(%(case)r)
 d = torch.device("cuda", 0)
 torch.cuda.set_device(d)
 p = planmod.build_plan(g.A, g.partvec, rank, k, g.f, device=d)
-used = p.init_comm(transport="p2p")
+used = p.init_comm(transport="p2p", nccl_fallback=False)
 assert used == "p2p", used
 own = p.lp.owned
 Hd = torch.from_numpy(g.H[own]).to(d).requires_grad_(True)
