@@ -146,6 +146,10 @@ int pgcn_comm_init(pgcn_plan* plan, const void* id128);
  *   pgcn_p2p_import : takes the k handles/layouts gathered from all ranks (rank-major)
  */
 #define PGCN_P2P_HANDLE_BYTES 512
+/* Many plans, one communicator (mini-batch training: one plan per pre-sampled batch, GPU/PGCN-Mini-batch.py:220-230
+ * swaps [bA, send_map, recv_map] per batch over the same process group): `plan` borrows `owner`'s NCCL communicator
+ * (same rank / size / device); the owner must outlive the borrowers. */
+int pgcn_comm_share(pgcn_plan* plan, pgcn_plan* owner);
 int pgcn_p2p_export(pgcn_plan* plan, void* handle_out);
 int pgcn_p2p_import(pgcn_plan* plan, const void* handles_k);
 
@@ -192,6 +196,9 @@ int pgcn_unpack_add(pgcn_plan* plan, const float* recv_slab, float* G_own, int32
  *   backward: G (m x f) = (A_local^T * gZ)[own] + contributions received from the peers.
  * With k == 1 no communicator is needed.
  */
+/* Plan option "relu" = 1 fuses the layer epilogue into the forward: Z = max(0, A_local * H), clamped in the store of
+ * whichever launch writes a row last (no extra pass over Z). With the dense step applied first — relu(A (H W)) — it is
+ * the reference layer relu(linear(PSpMM(A, H))) of GPU/PGCN.py:144-148 up to fp32 association. Forward only. */
 int pgcn_forward(pgcn_plan* plan, const float* H_own, float* Z, int32_t f, void* stream);
 int pgcn_backward(pgcn_plan* plan, const float* gZ, float* G_own, int32_t f, void* stream);
 

@@ -17,7 +17,7 @@ SYMBOLS = [
     "pgcn_version", "pgcn_device_count", "pgcn_last_error",
     "pgcn_plan_create", "pgcn_plan_destroy", "pgcn_plan_set_option", "pgcn_plan_get_option",
     "pgcn_plan_autotune", "pgcn_debug_schedule", "pgcn_plan_slab", "pgcn_algorithmic_bytes", "pgcn_launch_count",
-    "pgcn_comm_unique_id", "pgcn_comm_init", "pgcn_p2p_export", "pgcn_p2p_import",
+    "pgcn_comm_unique_id", "pgcn_comm_init", "pgcn_comm_share", "pgcn_p2p_export", "pgcn_p2p_import",
     "pgcn_spmm", "pgcn_pack", "pgcn_exchange", "pgcn_unpack_add",
     "pgcn_forward", "pgcn_backward", "pgcn_forward_host", "pgcn_forward_host_async", "pgcn_forward_host_wait",
 ]
@@ -101,6 +101,8 @@ def load(build_if_missing=True):
     lib.pgcn_backward.argtypes = [vp, vp, vp, i32, vp]
     lib.pgcn_forward_host.restype = C.c_int
     lib.pgcn_forward_host.argtypes = [vp, vp, vp, i32]
+    lib.pgcn_comm_share.restype = C.c_int
+    lib.pgcn_comm_share.argtypes = [vp, vp]
     lib.pgcn_forward_host_async.restype = C.c_int
     lib.pgcn_forward_host_async.argtypes = [vp, vp, vp, i32]
     lib.pgcn_forward_host_wait.restype = C.c_int

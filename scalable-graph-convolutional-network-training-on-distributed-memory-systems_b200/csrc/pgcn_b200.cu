@@ -84,6 +84,7 @@ struct DevCsr {
     bool view = false;              // a row range of another matrix: d_cw / d_rowids / d_empty are borrowed
     int row_base = 0;               // compact id of the first walked row (views: offset into the parent's numbering)
     std::vector<int> h_rowids, h_empty;   // host copies (parents of views only)
+    unsigned char* d_final = nullptr;     // per walked row: this matrix is the LAST launch of the forward that writes it
     int64_t tuned_epb[2] = {0, 0};  // per-matrix autotune results (0: use the plan option): [0] register, [1] ring
     int tuned_slots = 0;
     // schedules: [0] register-pipeline kernel (small row blocks, one per lane group),
@@ -139,6 +140,7 @@ struct pgcn_plan {
 
     // options
     int64_t opt_epb = 128, opt_long = 0, opt_tile = 0, opt_overlap = 1, opt_hot_mb = 64;
+    int64_t opt_relu = 0;            // fused layer epilogue of pgcn_forward: Z = max(0, A_local * H)
     // kernel: 0 auto (ring with TMA bulk copies where it applies), 4 register pipeline, 5 ring/1-D TMA,
     //         6 ring/cp.async, 7 ring/TMA tile::gather4 (= auto)
     int64_t opt_ring_groups = 2;
@@ -150,6 +152,7 @@ struct pgcn_plan {
 
     // NCCL
     ncclComm_t comm = nullptr;
+    bool comm_borrowed = false;            // pgcn_comm_share: the communicator belongs to another plan
     cudaStream_t comm_stream = nullptr;
     cudaStream_t host_stream = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
@@ -287,6 +290,7 @@ void csr_view(const DevCsr& base, DevCsr& v, int r0, int r1)
 void csr_free(DevCsr& c)
 {
     if (!c.view) { cudaFree(c.d_cw); cudaFree(c.d_rowids); cudaFree(c.d_empty); }
+    cudaFree(c.d_final);
     for (auto& sc : c.sched) { cudaFree(sc.d_blocks); cudaFree(sc.d_long); cudaFree(sc.d_partial); }
     c = DevCsr();
 }
@@ -510,7 +514,7 @@ bool use_ring(const pgcn_plan* p, const float* H0, const float* H1, int f)
 }
 
 int launch_spmm(pgcn_plan* p, DevCsr& c, const float* H0, const float* H1, int split,
-                float* Z0, float* Z1, int zsplit, int f, int beta, cudaStream_t st)
+                float* Z0, float* Z1, int zsplit, int f, int beta, cudaStream_t st, int relu = 0, bool use_final = false)
 {
     if (c.nrows == 0) return 0;
     const bool ring = use_ring(p, H0, H1, f) && aligned16(Z0) && aligned16(Z1);
@@ -542,6 +546,7 @@ int launch_spmm(pgcn_plan* p, DevCsr& c, const float* H0, const float* H1, int s
     a.Z0 = Z0; a.Z1 = Z1; a.zsplit = zsplit;
     a.rowids = c.d_rowids;
     a.partial = sc.d_partial; a.f = f; a.beta = beta;
+    a.relu = relu; a.final = (relu && use_final) ? c.d_final : nullptr;
     if (sc.nblocks > 0 && ring) {
         const int vpl = (f % 256 == 0) ? 2 : 1;
         const int tiles = f / (128 * vpl);
@@ -598,6 +603,7 @@ int launch_spmm(pgcn_plan* p, DevCsr& c, const float* H0, const float* H1, int s
         FixupArgs fa;
         fa.long_rows = sc.d_long; fa.nlong = sc.nlong; fa.partial = sc.d_partial;
         fa.Z0 = Z0; fa.Z1 = Z1; fa.zsplit = zsplit; fa.rowids = c.d_rowids; fa.f = f; fa.beta = beta;
+        fa.relu = a.relu; fa.final = a.final;
         const int nvec = f / t.vw;
         const unsigned grid = (unsigned)sc.nlong * (unsigned)((nvec + 31) / 32);
         if (t.vw == 4) spmm_fixup_kernel<4><<<grid, 32 * kFixupGroups, 0, st>>>(fa);
@@ -814,12 +820,35 @@ int pgcn_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* 
             for (int q = 0; q < k; ++q)
                 if (touched[q]) { q_map[q].push_back(r); q_rp[q].push_back((int)q_ci[q].size()); touched[q] = 0; }
         }
-        TRY(csr_upload(p, p->own, m, o_rp.data(), o_ci.data(), o_v.data(), nullptr, refs_fwd.data(), cold_fwd));
+        TRY(csr_upload(p, p->own, m, o_rp.data(), o_ci.data(), o_v.data(), nullptr, refs_fwd.data(), cold_fwd, true));
         p->halo_q.resize((size_t)k);
         for (int q = 0; q < k; ++q) {
             if (q_map[q].empty()) continue;
             TRY(csr_upload(p, p->halo_q[q], (int)q_map[q].size(), q_rp[q].data(), q_ci[q].data(), q_v[q].data(), &q_map[q],
                            refs_fwd.data() + m, cold_fwd));
+        }
+        // fused ReLU epilogue: a row is clamped by the launch of the pipelined forward that writes it last — the
+        // own-columns launch for rows without halo entries, else the last peer block (in this rank's step order)
+        {
+            std::vector<int> last_step((size_t)m, 0);
+            for (int i = 1; i < k; ++i) {
+                const int src = (rank - i + k) % k;
+                for (int r : q_map[src]) last_step[(size_t)r] = i;
+            }
+            std::vector<unsigned char> fin;
+            fin.resize((size_t)std::max(p->own.nrows_c, 1));
+            for (int c = 0; c < p->own.nrows_c; ++c) {
+                const int r = p->own.d_rowids ? p->own.h_rowids[(size_t)c] : c;
+                fin[(size_t)c] = last_step[(size_t)r] == 0;
+            }
+            TRY(upload(p, &p->own.d_final, fin.data(), fin.size()));
+            for (int i = 1; i < k; ++i) {
+                const int src = (rank - i + k) % k;
+                if (q_map[src].empty()) continue;
+                fin.resize(q_map[src].size());
+                for (size_t j = 0; j < q_map[src].size(); ++j) fin[j] = last_step[(size_t)q_map[src][j]] == i;
+                TRY(upload(p, &p->halo_q[(size_t)src].d_final, fin.data(), fin.size()));
+            }
         }
         csr_view(p->tr, p->tr_own, 0, m);
         p->tr_halo_q.resize((size_t)k);
@@ -886,7 +915,7 @@ int pgcn_plan_destroy(pgcn_plan* p)
     if (!p) return 0;
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
-    if (p->comm && g_nccl.ok) g_nccl.CommDestroy(p->comm);
+    if (p->comm && g_nccl.ok && !p->comm_borrowed) g_nccl.CommDestroy(p->comm);
     for (int q = 0; q < kMaxPeers; ++q)
         if (p->peer_arena[q] && q != p->rank && !p->peer_local[q]) cudaIpcCloseMemHandle(p->peer_arena[q]);
     cudaFree(p->arena);
@@ -942,6 +971,7 @@ int pgcn_plan_set_option(pgcn_plan* p, const char* name, int64_t value)
         // silent no-op, so it is refused (use the PGCN_HOT_MB environment variable before creating the plan)
         return fail(p, PGCN_ERR_STATE, "hot_mb is fixed at plan creation (set PGCN_HOT_MB before pgcn_plan_create)");
     else if (n == "overlap") p->opt_overlap = value;
+    else if (n == "relu") p->opt_relu = value ? 1 : 0;
     else if (n == "p2p") {
         // 0 = never use the peer transport even though pgcn_p2p_import succeeded here (another rank could not map
         // its peers: every rank must then fall back to NCCL together); 1 re-enables it when the arenas are mapped.
@@ -967,6 +997,7 @@ int64_t pgcn_plan_get_option(const pgcn_plan* p, const char* name)
     if (n == "tile_floats") return p->opt_tile;
     if (n == "hot_mb") return p->opt_hot_mb;
     if (n == "overlap") return p->opt_overlap;
+    if (n == "relu") return p->opt_relu;
     if (n == "p2p") return p->p2p ? 1 : 0;
     if (n == "nccl") return p->comm ? 1 : 0;
     if (n == "blocks_fwd") return p->fwd.sched[0].nblocks;
@@ -1127,6 +1158,18 @@ int pgcn_comm_init(pgcn_plan* p, const void* id128)
     return 0;
 }
 
+int pgcn_comm_share(pgcn_plan* p, pgcn_plan* owner)
+{
+    if (!p || !owner) return fail(p, PGCN_ERR_INVALID, "null argument");
+    if (!owner->comm) return fail(p, PGCN_ERR_STATE, "the owner plan has no communicator (pgcn_comm_init first)");
+    if (p->k != owner->k || p->rank != owner->rank || p->device != owner->device)
+        return fail(p, PGCN_ERR_INVALID, "plans of different rank / size / device cannot share a communicator");
+    if (p->comm && !p->comm_borrowed) return fail(p, PGCN_ERR_STATE, "plan already owns a communicator");
+    p->comm = owner->comm;
+    p->comm_borrowed = true;
+    return 0;
+}
+
 int pgcn_p2p_export(pgcn_plan* p, void* handle_out)
 {
     if (!p || !handle_out) return fail(p, PGCN_ERR_INVALID, "null argument");
@@ -1266,8 +1309,9 @@ int pgcn_forward(pgcn_plan* p, const float* H_own, float* Z, int32_t f, void* st
     if (rc) return rc;
     if (p->m > 0 && (!H_own || !Z)) return fail(p, PGCN_ERR_INVALID, "null H_own/Z");
     cudaStream_t st = (cudaStream_t)stream;
+    const int relu = (int)p->opt_relu;
     if (p->k == 1)
-        return launch_spmm(p, p->fwd, H_own, p->h > 0 ? p->d_halo_slab : nullptr, p->m, Z, nullptr, p->m, f, 0, st);
+        return launch_spmm(p, p->fwd, H_own, p->h > 0 ? p->d_halo_slab : nullptr, p->m, Z, nullptr, p->m, f, 0, st, relu);
 
     const bool use_p2p = p->p2p && (f % 4 == 0);
     if (!use_p2p && !p->comm) return fail(p, PGCN_ERR_STATE, "k=%d: call pgcn_comm_init or pgcn_p2p_import first", p->k);
@@ -1302,16 +1346,16 @@ int pgcn_forward(pgcn_plan* p, const float* H_own, float* Z, int32_t f, void* st
         if (use_p2p)
             for (int i = 1; i < k; ++i)
                 if ((rc = p2p_wait(p, step_src(p, i), st))) return rc;
-        return launch_spmm(p, p->fwd, H_own, p->h > 0 ? halo : nullptr, p->m, Z, nullptr, p->m, f, 0, st);
+        return launch_spmm(p, p->fwd, H_own, p->h > 0 ? halo : nullptr, p->m, Z, nullptr, p->m, f, 0, st, relu);
     }
     // ---- compute side: own columns while the rows travel, then each source's block as soon as it has landed
-    if ((rc = launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, f, 0, st))) return rc;
+    if ((rc = launch_spmm(p, p->own, H_own, nullptr, p->m, Z, nullptr, p->m, f, 0, st, relu, true))) return rc;
     for (int i = 1; i < k; ++i) {
         const int src = step_src(p, i);
         if (use_p2p) { if ((rc = p2p_wait(p, src, st))) return rc; }
         else CU(p, cudaStreamWaitEvent(st, p->ev_step[(size_t)i], 0));
         if (p->halo_q[(size_t)src].nrows == 0) continue;
-        if ((rc = launch_spmm(p, p->halo_q[(size_t)src], halo, nullptr, p->h, Z, nullptr, p->m, f, 1, st))) return rc;
+        if ((rc = launch_spmm(p, p->halo_q[(size_t)src], halo, nullptr, p->h, Z, nullptr, p->m, f, 1, st, relu, true))) return rc;
     }
     if (use_p2p) CU(p, cudaStreamWaitEvent(st, p->ev_b, 0));
     return 0;

@@ -65,7 +65,15 @@ struct SpmmArgs {
     float* partial;          // side buffer for split rows, row stride f
     int f;                   // feature width == leading dimension of H0/H1/Z0/Z1/partial
     int beta;                // 0: Z = A*H ; 1: Z += A*H
+    // fused layer epilogue (GPU/PGCN.py:144-148 applies relu after the aggregation + dense step): when `relu` is set
+    // a row is clamped at zero by the launch that writes it LAST — every row of a single-pass launch
+    // (final == nullptr), else the rows whose byte in `final` (indexed by the walked row id) is non-zero
+    int relu;
+    const unsigned char* final;
 };
+
+__device__ __forceinline__ float4 vrelu(const float4& a) { return make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f)); }
+__device__ __forceinline__ float vrelu(const float& a) { return fmaxf(a, 0.f); }
 
 template <int VW> struct Vec;
 template <> struct Vec<4> { typedef float4 type; };
@@ -209,6 +217,7 @@ spmm_rowblock_kernel(const SpmmArgs a)
     auto flush_row = [&]() {
         // write the finished row, clear the accumulator, advance to the next row of the block
         const int orow = (a.rowids != nullptr) ? __ldg(a.rowids + row) : row;
+        const bool relu_row = a.relu && (a.final == nullptr || __ldg(a.final + row) != 0);
         char* zb = (orow < a.zsplit)
                        ? reinterpret_cast<char*>(a.Z0) + (size_t)(unsigned)orow * pitch
                        : reinterpret_cast<char*>(a.Z1) + (size_t)(unsigned)(orow - a.zsplit) * pitch;
@@ -218,6 +227,7 @@ spmm_rowblock_kernel(const SpmmArgs a)
             if (fok[v]) {
                 vec_t* zp = reinterpret_cast<vec_t*>(zb + v * LPE * VW * 4);
                 if (a.beta) vadd(acc[v], *zp);
+                if (relu_row) acc[v] = vrelu(acc[v]);
                 st_out(zp, acc[v]);
             }
             acc[v] = vzero((vec_t*)nullptr);
@@ -338,6 +348,7 @@ struct FixupArgs {
     float* Z0; float* Z1; int zsplit;
     const int* rowids;
     int f; int beta;
+    int relu; const unsigned char* final;
 };
 
 // One CTA per (split row, chunk of 32 vectors): 8 warps each sum every 8th segment (independent
@@ -382,6 +393,7 @@ spmm_fixup_kernel(const FixupArgs a)
         float* zrow = (orow < a.zsplit) ? a.Z0 + (size_t)orow * a.f : a.Z1 + (size_t)(orow - a.zsplit) * a.f;
         vec_t* zp = reinterpret_cast<vec_t*>(zrow) + v;
         if (a.beta) vadd(t, *zp);
+        if (a.relu && (a.final == nullptr || __ldg(a.final + d.x) != 0)) t = vrelu(t);
         *zp = t;
     }
 }

@@ -78,18 +78,21 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // out of line keeps the hot loop inside the instruction cache (the rows-end path runs once per ~17 edges).
 template <int VPL>
 __device__ __noinline__ void ring_store_row(float4 a0, float4 a1, const int* rowids, int row, float* Z0, float* Z1,
-                                            int zsplit, size_t pitch, size_t off, int beta)
+                                            int zsplit, size_t pitch, size_t off, int beta, int relu, const unsigned char* final)
 {
+    const bool relu_row = relu && (final == nullptr || __ldg(final + row) != 0);
     const int orow = (rowids != nullptr) ? __ldg(rowids + row) : row;
     char* zb = (orow < zsplit) ? reinterpret_cast<char*>(Z0) + (size_t)(unsigned)orow * pitch
                                : reinterpret_cast<char*>(Z1) + (size_t)(unsigned)(orow - zsplit) * pitch;
     zb += off;
     float4* zp = reinterpret_cast<float4*>(zb);
     if (beta) vadd(a0, *zp);
+    if (relu_row) a0 = vrelu(a0);
     st_out(zp, a0);
     if (VPL == 2) {
         float4* zq = reinterpret_cast<float4*>(zb + 512);
         if (beta) vadd(a1, *zq);
+        if (relu_row) a1 = vrelu(a1);
         st_out(zq, a1);
     }
 }
@@ -237,7 +240,7 @@ __device__ __forceinline__ void ring_body(const SpmmArgs& a, const RingArgs& ra,
             fetch_piece();
         };
         auto flush_row = [&]() {
-            ring_store_row<VPL>(acc[0], acc[VPL - 1], a.rowids, row, a.Z0, a.Z1, a.zsplit, pitch, toff + lane * 16, a.beta);
+            ring_store_row<VPL>(acc[0], acc[VPL - 1], a.rowids, row, a.Z0, a.Z1, a.zsplit, pitch, toff + lane * 16, a.beta, a.relu, a.final);
 #pragma unroll
             for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
             ++row;

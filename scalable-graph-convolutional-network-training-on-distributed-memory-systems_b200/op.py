@@ -36,14 +36,21 @@ def _check_feat(plan, H, rows, what):
     return H.contiguous()
 
 
-def aggregate_forward(plan, H_own):
-    """Z_own = (A * H)[owned rows]; H_own, Z_own are [m, f]."""
+def aggregate_forward(plan, H_own, relu=False):
+    """Z_own = (A * H)[owned rows]; H_own, Z_own are [m, f]. relu=True: Z_own = max(0, .), clamped inside the store of
+    the launch that writes each row last (plan option "relu")."""
     H_own = _check_feat(plan, H_own, plan.m, "H")
     f = H_own.shape[1]
     Z = torch.empty((plan.m, f), dtype=torch.float32, device=H_own.device)
     lib = cabi.load()
     with torch.cuda.device(H_own.device):
-        cabi.check(lib.pgcn_forward(plan.handle, H_own.data_ptr(), Z.data_ptr(), f, _stream_ptr()), plan.handle)
+        if relu:
+            plan.set_option("relu", 1)
+        try:
+            cabi.check(lib.pgcn_forward(plan.handle, H_own.data_ptr(), Z.data_ptr(), f, _stream_ptr()), plan.handle)
+        finally:
+            if relu:
+                plan.set_option("relu", 0)
     if plan.lp.k > 1:
         plan.count_exchange(backward=False)
     return Z
@@ -86,6 +93,25 @@ class PSpMM(torch.autograd.Function):
             G.index_copy_(0, A.owned_index(), G_own)
             return None, G
         return None, aggregate_backward(A, grad_output)
+
+
+class PSpMMRelu(torch.autograd.Function):
+    """relu(A * X) with the clamp fused into the aggregation's output store. Feeding it
+    X = linear(H) gives the reference layer relu(linear(PSpMM(A, H))) of GPU/PGCN.py:144-148 up to fp32 association
+    ((A H) W^T == A (H W^T)); the dense step then also runs before the aggregation instead of after it.
+    Backward: relu's mask comes from the saved output (out > 0), then the regular PSpMM backward."""
+
+    @staticmethod
+    def forward(ctx, A, X):
+        ctx.plan = A
+        out = aggregate_forward(A, X, relu=True)
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (out,) = ctx.saved_tensors
+        return None, aggregate_backward(ctx.plan, grad_output * (out > 0))
 
 
 # ---- the pieces, individually callable (NCCL transport), mirroring communicate_fgm ----------------

@@ -30,7 +30,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import graphio, plan as planmod
-from .op import PSpMM, communicate_fgm, spmm_local, aggregate_backward
+from .op import PSpMM, PSpMMRelu, communicate_fgm, spmm_local, aggregate_backward
 
 
 class _PSpMMQuirkQ1(torch.autograd.Function):
@@ -51,13 +51,17 @@ class _PSpMMQuirkQ1(torch.autograd.Function):
 class PGCN(nn.Module):
     """GPU/PGCN.py:136-148 with the plan handle in place of the sparse tensor."""
 
-    def __init__(self, A, in_features, out_features, quirk_q1=False):
+    def __init__(self, A, in_features, out_features, quirk_q1=False, fused=False):
         super().__init__()
         self.linear = nn.Linear(in_features, out_features, bias=False)
         self.A = A
         self.quirk_q1 = quirk_q1
+        self.fused = fused and not quirk_q1
 
     def forward(self, H):
+        if self.fused:
+            # relu(A (H W^T)): dense step on the m owned rows first, relu fused into the aggregation's store
+            return PSpMMRelu.apply(self.A, self.linear(H))
         H = _PSpMMQuirkQ1.apply(self.A, H) if self.quirk_q1 else PSpMM.apply(self.A, H)
         H = self.linear(H)
         return F.relu(H)
@@ -84,7 +88,7 @@ def reference_loss(logits_own, labels_own, n):
 
 
 def run(rank, size, nlayers, nfeatures, path_A, path_partvec, backend, ref_quirks=False, transport="auto",
-        out=sys.stdout, seed=None):
+        out=sys.stdout, seed=None, fused=False):
     if backend != "nccl":
         raise RuntimeError("backend '%s': the B200 PGCN path runs on CUDA devices over NCCL/NVLink only "
                            "(no CPU fallback); use -b nccl" % backend)
@@ -112,7 +116,7 @@ def run(rank, size, nlayers, nfeatures, path_A, path_partvec, backend, ref_quirk
 
     if seed is not None:
         torch.manual_seed(seed)
-    model = nn.Sequential(*[PGCN(plan, nfeatures, nfeatures, quirk_q1=(ref_quirks and i == 0))
+    model = nn.Sequential(*[PGCN(plan, nfeatures, nfeatures, quirk_q1=(ref_quirks and i == 0), fused=fused)
                             for i in range(nlayers)]).to(device)        # :194-198
     if size > 1:
         initialize_parameters(model, size)
@@ -172,7 +176,7 @@ def main(argv):
     rank = int(os.environ.get("SLURM_PROCID", os.environ.get("RANK", "0")))
     os.environ["RANK"] = str(rank)
     try:
-        opts, _ = getopt.getopt(argv, "a:p:b:s:l:f:", ["ref-quirks", "transport=", "seed="])
+        opts, _ = getopt.getopt(argv, "a:p:b:s:l:f:", ["ref-quirks", "transport=", "seed=", "fused"])
     except getopt.GetoptError:
         print("a:p:b:", flush=True)                                       # the reference's usage text, :264
         sys.exit(2)
@@ -199,6 +203,8 @@ def main(argv):
             kw["transport"] = arg
         elif opt == "--seed":
             kw["seed"] = int(arg)
+        elif opt == "--fused":
+            kw["fused"] = True           # relu(A (H W^T)) with the clamp fused into the aggregation
     if path_A is None or path_partvec is None or nlayers is None or nfeatures is None:
         print("usage: PGCN.py -a <A.mtx> -p <partvec> -b nccl -s <nparts> -l <nlayers> -f <nfeatures>", flush=True)
         sys.exit(2)

@@ -340,6 +340,11 @@ class PgcnPlan:
             cabi.check(self._lib.pgcn_comm_init(self.handle, raw), self._h)
         return used or "nccl"
 
+    def share_comm(self, owner):
+        """Borrow `owner`'s NCCL communicator (one plan per mini-batch over one process group)."""
+        cabi.check(self._lib.pgcn_comm_share(self.handle, owner.handle), self._h)
+        self._comm_owner = owner          # keep it alive
+
     # -- stats, as the reference counts them (rows, messages incl. empty ones) -------------------
     def count_exchange(self, backward=False):
         lp = self.lp

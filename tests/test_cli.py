@@ -95,3 +95,35 @@ def test_cli_multi_rank_matches_reference(tmp_path, k):
     assert out0["total_vol"] == ref["total_vol"] and out0["total_nmsg"] == ref["total_nmsg"]
     assert "total_vol: %d total_nmsg: %d" % (ref["total_vol"], ref["total_nmsg"]) in text0
     np.testing.assert_allclose(out0["losses"], ref["losses"], rtol=1e-3 if k == 2 else 5e-2)
+
+
+@pytest.mark.gpu
+def test_minibatch_driver_matches_reference_losses(tmp_path):
+    """the mini-batch trainer (one plan per pre-sampled batch, swapped per step) against the
+    loss curve of the UNMODIFIED GPU/PGCN-Mini-batch.py run() on karate (tests/golden/make_minibatch_e2e_golden.py:
+    one rank, 3 layers, f = 4, batch_size = 12, seeded weights) — same sampling sequence, same per-batch
+    sub-matrices, same loss bookkeeping (epoch sums start at 1)."""
+    import io
+    import pickle
+    import shutil
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device")
+    from pgcn_b200 import minibatch
+    ref = json.load(open(os.path.join(GOLDEN, "karate_minibatch_e2e.json")))
+    z = np.load(os.path.join(GOLDEN, "karate_minibatch.npz"))
+    import scipy.sparse as sp
+    from scipy.io import mmwrite
+    n = int(z["n"])
+    A = sp.coo_matrix((z["val"], (z["row"], z["col"])), shape=(n, n))
+    a = str(tmp_path / "karate.mtx")
+    mmwrite(a, A)
+    pv = str(tmp_path / "pv1.pkl")
+    pickle.dump([0] * n, open(pv, "wb"))
+    buf = io.StringIO()
+    res = minibatch.run(0, 1, ref["layers"], ref["f"], a, pv, "nccl", ref["batch_size"], out=buf, seed=ref["seed"])
+    assert res["nbatches"] == (n // ref["batch_size"] + 1) * 3
+    np.testing.assert_allclose(res["losses"], ref["losses"], rtol=5e-4)
+    text = buf.getvalue()
+    assert "Epoch 00003 | Loss" in text and "total_vol: 0 total_nmsg: 0" in text
+    with pytest.raises(RuntimeError):
+        minibatch.run(0, 1, 3, 4, a, pv, "gloo", 12)

@@ -173,3 +173,95 @@ def test_more_ranks_than_the_peer_transport_takes():
     assert b"16" in cabi.load().pgcn_last_error(plans[0].handle)
     for p in plans:
         p.close()
+
+
+@pytest.mark.parametrize("case,k", [("karate_k3", 3), ("unsym_k4_rp", 4)])
+def test_operator_driven_from_the_cpu_partitioner_output(case, k):
+    """SURVEY.md §8f rank 4 closed on the GPU: the files the reference's CPU-path partitioner `gcnhgp` wrote
+    (A.k / H.k / conn.k / buff.k / config, GCN-HP/main.cpp:117-282) -> graphio.read_cpu_partition -> plans -> the
+    fused forward / backward over the peer transport (all ranks on this GPU), with the trainer's first-layer input
+    H0 = 1.0 on every owned row (Parallel-GCN/main.c:650-684). Checked rank by rank against the C restatement of
+    the GraphBLAS aggregation (AH = A*H on own rows, then += per received block, main.c:271,295) and the fp64 truth;
+    the exchanged row counts equal the reference's own buff.k counts where its connectivity rule applies (symmetric
+    pattern)."""
+    from oracle import build_oracle
+    d = os.path.join(ROOT, "tests", "golden", "cpu_path", case)
+    P = graphio.read_cpu_partition(d, k)
+    A, pv = P["A"].tocoo(), P["partvec"]
+    n = A.shape[0]
+    f = 4 * max(1, int(P["config"]["widths"][0]))            # a multiple of 4 so the peer-store kernels take it
+    plans = [planmod.build_plan(A, pv, r, k, f, device=dev()) for r in range(k)]
+    planmod.link_local_plans(plans)
+    H = np.ones((n, f), dtype=np.float32) * (1.0 + np.arange(f, dtype=np.float32)[None, :])   # H0 rows identical per column
+    G = np.random.RandomState(5).uniform(-1, 1, size=(n, f)).astype(np.float32)
+    Hd = [torch.from_numpy(H[p.lp.owned]).to(dev()) for p in plans]
+    Gd = [torch.from_numpy(G[p.lp.owned]).to(dev()) for p in plans]
+    Z = run_all(plans, "pgcn_forward", Hd, f)
+    Gr = run_all(plans, "pgcn_backward", Gd, f)
+    Z64 = orc.truth_forward(A, H); G64 = orc.truth_backward(A, G)
+    tolZ = fp32_tol(A, H, int(orc.row_degree(A).max())); tolG = fp32_tol(A.T, G, int(orc.row_degree(A.T).max()))
+    for r, p in enumerate(plans):
+        lp = p.lp
+        assert_close_fp32(Z[r].cpu().numpy(), Z64[lp.owned], tolZ[lp.owned], "%s fwd r%d" % (case, r))
+        assert_close_fp32(Gr[r].cpu().numpy(), G64[lp.owned], tolG[lp.owned], "%s bwd r%d" % (case, r))
+        Hcat = np.concatenate([H[lp.owned], H[lp.halo]], 0)
+        Zc = build_oracle.grb_aggregate(lp.rowptr, lp.colidx, lp.vals, Hcat, lp.recv_off, lp.m)
+        np.testing.assert_allclose(Z[r].cpu().numpy(), Zc, rtol=3e-5, atol=3e-6)
+        if case == "karate_k3":                                # symmetric: the reference's buff.k == the plan's counts
+            bs, br = P["buff"][r]
+            assert sum(bs.values()) == lp.S and sum(br.values()) == lp.h
+        p.close()
+
+
+@pytest.mark.parametrize("case", ["gemat11_k1", "gemat11_k3_hp", "rmat_k4"])
+def test_fused_relu_epilogue_equals_reference_layer(case):
+    """relu fused into the aggregation's store — relu(A (H W^T)) through pgcn_forward with the
+    plan option "relu" — equals the reference layer relu(linear(PSpMM(A, H))) (GPU/PGCN.py:144-148) computed in fp64,
+    on one rank (single pass), on 3 / 4 ranks with the per-peer pipelined forward (each row clamped by the launch that
+    writes it last) and without overlap; rows with a long neighbour list go through the split-row fixup; the
+    backward mask is relu's (out > 0)."""
+    from pgcn_b200.op import PSpMMRelu
+    if case == "rmat_k4":
+        n, f, k = 9000, 128, 4
+        A = graphio.synthetic_graph(n, 200000, seed=14)
+        pv = graphio.random_partvec(n, k, seed=3)
+        H = np.random.RandomState(2).uniform(-1, 1, size=(n, f)).astype(np.float32)
+    else:
+        g = Golden(case)
+        A, pv, H, f, k, n = g.A, g.partvec, g.H, g.f, g.k, g.n
+    W = np.random.RandomState(7).uniform(-0.5, 0.5, size=(f, f)).astype(np.float32)
+    X = (H.astype(np.float64) @ W.T.astype(np.float64)).astype(np.float32)          # the dense step, done first
+    pre64 = orc.truth_forward(A, X)                                                  # A (H W^T) in fp64
+    ref = np.maximum(pre64, 0.0)
+    tol = fp32_tol(A, X, int(orc.row_degree(A).max()))
+    plans = [planmod.build_plan(A, pv, r, k, f, device=dev()) for r in range(k)]
+    if k > 1:
+        planmod.link_local_plans(plans)
+    Xd = [torch.from_numpy(X[p.lp.owned]).to(dev()) for p in plans]
+    for overlap in (1, 0):
+        for p in plans:
+            p.set_option("overlap", overlap); p.set_option("relu", 1)
+            p.set_option("ring_edges_per_block", 64); p.set_option("edges_per_block", 16)   # force split rows
+        Z = run_all(plans, "pgcn_forward", Xd, f)
+        for r, p in enumerate(plans):
+            own = p.lp.owned
+            z = Z[r].cpu().numpy()
+            assert (z >= 0).all()
+            # exact zeros where the pre-activation is clearly negative, the fp32 bound elsewhere
+            assert_close_fp32(z, ref[own], tol[own], "%s fused relu r%d overlap=%d" % (case, r, overlap))
+            assert (z[pre64[own] < -tol[own]] == 0).all()
+            p.set_option("relu", 0)
+    if k == 1:
+        # autograd: d/dX of sum(relu(A X) * G) == A^T (G * mask)
+        Xt = Xd[0].clone().requires_grad_(True)
+        out = PSpMMRelu.apply(plans[0], Xt)
+        Gm = torch.from_numpy(np.random.RandomState(9).uniform(-1, 1, size=(n, f)).astype(np.float32)).to(dev())
+        out.backward(Gm)
+        mask = (pre64 > 0)
+        gref = orc.truth_backward(A, Gm.cpu().numpy() * mask)
+        sure = np.abs(pre64) > tol                                                    # mask bits fp32 cannot flip
+        if sure.all():
+            np.testing.assert_allclose(Xt.grad.cpu().numpy(), gref, rtol=1e-4, atol=1e-5 * max(1.0, np.abs(gref).max()))
+        assert plans[0].get_option("relu") == 0
+    for p in plans:
+        p.close()
