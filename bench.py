@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--cache", default=os.environ.get("PGCN_CACHE", "/tmp/pgcn_b200_cache"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lib-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer (e2e) measurement (side runs only)")
     ap.add_argument("--no-single", action="store_true", help="N > 1: skip the single-GPU run of the same config")
     ap.add_argument("--opt", action="append", default=[], help="plan option name=value (tuning)")
     args = ap.parse_args()
@@ -369,30 +370,34 @@ def main():
     # ---- e2e: host buffers through the C-ABI host entry points (software-pipelined: two device slots, the upload
     # of step i+1 and the download of step i-1 run under the aggregation of step i; every step's H goes host ->
     # device and every step's Z device -> host inside the timed region) --------------------------------------
-    Hh = [torch.empty((lp.m, f), dtype=torch.float32).pin_memory() for _ in range(2)]
-    Zh = [torch.empty((lp.m, f), dtype=torch.float32).pin_memory() for _ in range(2)]
+    if args.no_e2e:
+        s_e2e = s_e2e_serial = float("nan"); e2e_ok = None; n_e2e = 0
+    Hh = [] if args.no_e2e else [torch.empty((lp.m, f), dtype=torch.float32).pin_memory() for _ in range(2)]
+    Zh = [] if args.no_e2e else [torch.empty((lp.m, f), dtype=torch.float32).pin_memory() for _ in range(2)]
     for x in Hh:
         x.copy_(H)
-    n_e2e = max(4, min(args.steps, 12))
+    if not args.no_e2e:
+        n_e2e = max(4, min(args.steps, 12))
 
     def e2e_run(nsteps):
         for i in range(nsteps):
             cabi.check(lib.pgcn_forward_host_async(plan.handle, Hh[i & 1].data_ptr(), Zh[i & 1].data_ptr(), f), plan.handle)
         cabi.check(lib.pgcn_forward_host_wait(plan.handle), plan.handle)
 
-    e2e_run(2)
-    sync_all()
-    t0 = time.perf_counter()
-    e2e_run(n_e2e)
-    sync_all()
-    s_e2e = (time.perf_counter() - t0) / n_e2e
-    # the strictly serial form (one step at a time: copy in, aggregate, copy out, synchronise)
-    t0 = time.perf_counter()
-    for i in range(3):
-        cabi.check(lib.pgcn_forward_host(plan.handle, Hh[0].data_ptr(), Zh[0].data_ptr(), f), plan.handle)
-    sync_all()
-    s_e2e_serial = (time.perf_counter() - t0) / 3
-    e2e_ok = bool(torch.equal(Zh[0], Zh[1])) and bool(torch.isfinite(Zh[0][:16]).all())
+    if not args.no_e2e:
+        e2e_run(2)
+        sync_all()
+        t0 = time.perf_counter()
+        e2e_run(n_e2e)
+        sync_all()
+        s_e2e = (time.perf_counter() - t0) / n_e2e
+        # the strictly serial form (one step at a time: copy in, aggregate, copy out, synchronise)
+        t0 = time.perf_counter()
+        for i in range(3):
+            cabi.check(lib.pgcn_forward_host(plan.handle, Hh[0].data_ptr(), Zh[0].data_ptr(), f), plan.handle)
+        sync_all()
+        s_e2e_serial = (time.perf_counter() - t0) / 3
+        e2e_ok = bool(torch.equal(Zh[0], Zh[1])) and bool(torch.isfinite(Zh[0][:16]).all())
     del Hh, Zh
 
     # ---- reduce over ranks ---------------------------------------------------------------------
