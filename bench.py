@@ -259,6 +259,22 @@ def run_reference(args):
     return 0
 
 
+class QuietStdout:
+    """The contract is ONE JSON line on stdout: anything a library prints there while we work (NCCL's version banner
+    when the box sets NCCL_DEBUG) is sent to stderr instead; `emit` writes the line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(text, flush=True)
+        os.dup2(2, 1)
+
+
 def main():
     args = parse()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
@@ -270,6 +286,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    quiet = QuietStdout()
     import torch
     import torch.distributed as dist
     from pgcn_b200 import cabi, graphio, plan as planmod, op
@@ -500,7 +517,7 @@ def main():
                     line["roofline"]["traffic_source"] = "profiles/traffic_%s.json is stale (measured on other kernel sources)" % args.config
             except Exception:
                 pass
-        print(json.dumps(line), flush=True)
+        quiet.emit(json.dumps(line))
     plan.close()
     if world > 1:
         dist.barrier()
