@@ -510,9 +510,12 @@ def main():
         if os.path.exists(traffic_file) and world == 1:
             try:
                 tj = json.load(open(traffic_file))
-                if tj.get("source_hash") == source_hash():
+                cur = source_hash()
+                if cur == tj.get("source_hash") or cur in tj.get("accepted_hashes", []):
                     line["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
-                    line["roofline"]["traffic_source"] = "ncu dram__bytes_read+write per launch, %s" % tj.get("kernel", "")
+                    line["roofline"]["traffic_source"] = "ncu dram__bytes_read+write per launch, %s; measured on %s%s" % (
+                        tj.get("kernel", "")[:48], tj.get("measured_on_commit", "these sources")[:60],
+                        "" if cur == tj.get("source_hash") else " (later sources accepted by hand, see profiles/traffic_%s.json)" % args.config)
                 else:
                     line["roofline"]["traffic_source"] = "profiles/traffic_%s.json is stale (measured on other kernel sources)" % args.config
             except Exception:

@@ -144,6 +144,7 @@ struct pgcn_plan {
     // kernel: 0 auto (ring with TMA bulk copies where it applies), 4 register pipeline, 5 ring/1-D TMA,
     //         6 ring/cp.async, 7 ring/TMA tile::gather4 (= auto)
     int64_t opt_ring_groups = 2;
+    int64_t opt_persistent_multi = 0;
     int64_t opt_kernel = 0, opt_ring_slots = 16, opt_ring_epb = 512, opt_ring_long = 0, opt_persistent = 1;
     bool ring_attr_set[48] = {false};
     int ring_ctas_per_sm[48] = {0};
@@ -583,7 +584,13 @@ int launch_spmm(pgcn_plan* p, DevCsr& c, const float* H0, const float* H1, int s
         RingArgs ra;
         ra.counter = nullptr; ra.hub = nullptr; ra.nhub = 0;
         dim3 grid((unsigned)((sc.nblocks + kRingWarps - 1) / kRingWarps), (unsigned)tiles);
-        if (p->opt_persistent) {
+        // Persistent CTAs own their SM (shared memory + registers) until the whole launch is done; a put / NCCL kernel
+        // of the exchange stream would then wait behind the SpMM it is supposed to overlap (measured at 8 GPUs: step =
+        // sum of puts + sum of SpMMs). Multi-rank plans with overlap therefore run one block per warp (CTAs retire
+        // every few dozen microseconds and the higher-priority exchange kernels take the freed slots) unless
+        // `persistent_multi` asks otherwise.
+        const bool persistent = p->opt_persistent && (p->k == 1 || !p->opt_overlap || p->opt_persistent_multi);
+        if (persistent) {
             CU(p, cudaMemsetAsync(p->d_counter, 0, 64 * sizeof(unsigned int), st));
             ra.counter = p->d_counter;
             grid.x = std::min<unsigned>(grid.x, (unsigned)(p->num_sms * p->ring_ctas_per_sm[slot]));
@@ -963,6 +970,7 @@ int pgcn_plan_set_option(pgcn_plan* p, const char* name, int64_t value)
     else if (n == "ring_edges_per_block") p->opt_ring_epb = value;
     else if (n == "ring_long_row") p->opt_ring_long = value;
     else if (n == "persistent") p->opt_persistent = value;
+    else if (n == "persistent_multi") p->opt_persistent_multi = value;
     else if (n == "ring_groups") p->opt_ring_groups = value;
     else if (n == "long_row") p->opt_long = value;
     else if (n == "tile_floats") p->opt_tile = value;
@@ -992,6 +1000,7 @@ int64_t pgcn_plan_get_option(const pgcn_plan* p, const char* name)
     if (n == "ring_edges_per_block") return p->fwd.tuned_epb[1] > 0 ? p->fwd.tuned_epb[1] : p->opt_ring_epb;
     if (n == "ring_long_row") return p->opt_ring_long;
     if (n == "persistent") return p->opt_persistent;
+    if (n == "persistent_multi") return p->opt_persistent_multi;
     if (n == "ring_groups") return p->opt_ring_groups;
     if (n == "long_row") return p->opt_long;
     if (n == "tile_floats") return p->opt_tile;
