@@ -476,11 +476,15 @@ def main():
             "config": {
                 "workload": workload_name(args.config),
                 "partition": pv_name, "transport": transport, "l2": "inputs larger than L2 (H and Z %.0f MB each per rank)" % (lp.m * f * 4 / 1e6),
-                "plan_options": {k_: plan.get_option(k_) for k_ in ("edges_per_block", "long_row", "tile_floats", "overlap")},
+                "plan_options": {k_: plan.get_option(k_) for k_ in ("kernel", "ring_slots", "ring_groups", "ring_edges_per_block",
+                                                                    "persistent", "persistent_multi", "overlap", "relu")},
                 "nnz": nnz_total, "halo_rows_rank0": int(lp.h), "send_rows_rank0": int(lp.S),
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "spmm_rowblock_kernel", "ms_per_launch": ms_kernel,
+                         "traffic": None,
+                         "kernel": ("spmm_ring_g4_kernel (TMA tile::gather4 into per-warp shared-memory row rings)"
+                                    if f % 128 == 0 else "spmm_rowblock_kernel (register pipeline)"),
+                         "ms_per_launch": ms_kernel,
                          "algorithmic_bytes_per_launch": bytes_per_rank, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": nnz_total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),

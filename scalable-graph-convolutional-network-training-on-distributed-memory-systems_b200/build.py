@@ -1,6 +1,6 @@
 """Build the native pieces in-tree (so the .so files travel to the GPU box with the snapshot).
 
-  lib/libpgcn_b200.so   csrc/pgcn_b200.cu   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
+  lib/libpgcn_b200.so   csrc/pgcn_b200.cu (+ spmm_kernels.cuh, spmm_ring.cuh)   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
   (the CPU oracle under oracle/ is built by oracle/build_oracle.py — test infrastructure only)
 
 nvcc cross-compiles without a GPU; `python -m <pkg>.build` or `__graft_entry__.build()` runs this.
@@ -19,7 +19,8 @@ LIBDIR = os.path.join(HERE, "lib")
 _VARIANT = os.environ.get("PGCN_B200_VARIANT", "")
 LIB = os.path.join(LIBDIR, "libpgcn_b200%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 SOURCES = [os.path.join(CSRC, "pgcn_b200.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "spmm_kernels.cuh"), os.path.join(ROOT, "include", "pgcn_b200.h")]
+DEPS = SOURCES + [os.path.join(CSRC, "spmm_kernels.cuh"), os.path.join(CSRC, "spmm_ring.cuh"),
+                  os.path.join(ROOT, "include", "pgcn_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
