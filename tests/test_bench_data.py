@@ -51,3 +51,19 @@ def test_bench_picks_config_and_partition_like_the_docs_say():
     assert bench.part_vector(a8, n, 8)[1].startswith("rp")
     assert bench.part_vector(a1, graphio.CONFIGS["C2"][0], 1)[1] == "single part"
     assert len(bench.source_hash()) == 16
+
+
+def test_shipped_vector_belongs_to_the_generated_graph(tmp_path):
+    """The part vectors are only meaningful for the exact graph graphio generates: recompute the halo volume of
+    C2 / k = 8 / hp from a freshly generated C2 and compare with the number the partitioner tool reported when the
+    vector was made (any change of the generator's output would break this)."""
+    import re
+    from pgcn_b200 import graphio
+    z = np.load(os.path.join(ROOT, "bench_data", "C2.8.hp.npz"))
+    reported = int(re.search(r"halo rows total=(\d+)", str(z["report"])).group(1))
+    A = graphio.config_graph("C2", cache_dir=None).tocoo()
+    pv = z["partvec"].astype(np.int64)
+    prow, pcol = pv[A.row], pv[A.col]
+    cross = prow != pcol
+    keys = np.unique(prow[cross] * A.shape[0] + A.col[cross])
+    assert keys.shape[0] == reported
