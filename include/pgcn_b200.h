@@ -95,14 +95,27 @@ int pgcn_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* 
 int pgcn_plan_destroy(pgcn_plan* plan);
 
 /*
- * Scheduling tunables (take effect at the next compute call). Names:
- *   "edges_per_block"  target nnz handled by one lane group              (default 128)
- *   "long_row"         rows with more nnz than this are split            (default 4*edges_per_block)
- *   "tile_floats"      feature-tile width in floats, 0 = whole row       (default 0)
- *   "overlap"          1 = split A_local into own/halo column parts and overlap the exchange
- *                      with the own part (Parallel-GCN/main.c:271 then :295)   (default 1)
+ * Plan options (take effect at the next compute call). Names:
+ *   "kernel"               0 = automatic (default): widths that are multiples of 128 floats with 16-byte aligned
+ *                          operands take the shared-memory ring kernel fed by TMA tile::gather4, everything else the
+ *                          register-pipeline kernel; 4 = always the register kernel; 5 / 6 / 7 = ring kernel fed by
+ *                          1-D cp.async.bulk / cp.async / tile::gather4
+ *   "ring_slots"           row slots per warp of the ring kernel: 16 (default), 32, 64; "ring_groups" 2 | 4 (64 slots)
+ *   "ring_edges_per_block" target nnz of one row block = one warp's unit of work          (default 512)
+ *   "ring_long_row"        rows with more nnz than this are split into segments           (default 2 * block)
+ *   "persistent"           1 = persistent CTAs fetch row blocks dynamically (default; single-rank plans and plans
+ *                          without overlap), "persistent_multi" 1 = also for overlapped multi-rank plans (default 0:
+ *                          persistent CTAs would hold the SMs the exchange kernels need)
+ *   "edges_per_block", "long_row", "tile_floats"   the same for the register kernel (defaults 128, 4 * block, 0)
+ *   "overlap"              1 = split A_local into own / per-peer halo blocks and pipeline the exchange with them
+ *                          (Parallel-GCN/main.c:271 then :275-299)                         (default 1)
+ *   "relu"                 1 = pgcn_forward writes max(0, A_local * H)                      (default 0)
+ *   "p2p"                  0 = never use the peer-memory transport (all ranks must agree)  (default 1)
+ * pgcn_plan_autotune overrides block sizes / ring depth per matrix; setting one of them explicitly clears the tuned
+ * values. "hot_mb" (L2-resident hot set of H rows) is fixed at plan creation: environment variable PGCN_HOT_MB.
  * Split rows are always reduced in a fixed order: results are run-to-run deterministic.
- * Read-only names for pgcn_plan_get_option: "p2p", "nccl", "blocks_fwd", "long_rows_fwd".
+ * Read-only names for pgcn_plan_get_option: "nccl", "blocks_fwd", "long_rows_fwd", "ring_blocks_fwd",
+ * "ring_long_rows_fwd".
  */
 int pgcn_plan_set_option(pgcn_plan* plan, const char* name, int64_t value);
 int64_t pgcn_plan_get_option(const pgcn_plan* plan, const char* name);
